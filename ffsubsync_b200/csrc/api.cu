@@ -1,0 +1,501 @@
+// C-ABI entry points (include/ffsubsync_b200.h): handle lifecycle, workspace management and
+// the host<->device staging that turns B2_HOST calls into the device path.  All arithmetic
+// lives in the kernels (vad.cu, raster.cu, corr.cu, select.cu); nothing here computes results
+// on the CPU.
+#include <math.h>
+
+#include <algorithm>
+
+#include "common.cuh"
+
+extern "C" int b2_version(void) { return 100; }
+
+static uint64_t compute_log2_quirk_mask() {
+  // CPython: total_bits = math.log(n, 2) == log(n)/log(2) in double; ceil() of that is k+1 for
+  // some exact powers of two (k = 29, 31, 39, ... with glibc).  Reproduced with the same libm.
+  uint64_t mask = 0;
+  for (int k = 0; k < 63; ++k) {
+    double v = log((double)(1ULL << k)) / log(2.0);
+    if (ceil(v) > (double)k) mask |= (1ULL << k);
+  }
+  return mask;
+}
+
+extern "C" int b2_create(int device, b2_handle* out) {
+  if (!out) return B2_ERR_BAD_ARG;
+  *out = nullptr;
+  int count = 0;
+  if (cudaGetDeviceCount(&count) != cudaSuccess || device < 0 || device >= count)
+    return B2_ERR_CUDA;
+  b2_ctx* h = new b2_ctx();
+  h->device = device;
+  if (cudaSetDevice(device) != cudaSuccess) { delete h; return B2_ERR_CUDA; }
+  cudaDeviceProp prop;
+  if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) { delete h; return B2_ERR_CUDA; }
+  h->sm_count = prop.multiProcessorCount;
+  if (prop.major != 10) {  // built for sm_100a only: fail loudly instead of falling back
+    delete h;
+    return B2_ERR_UNSUPPORTED;
+  }
+  if (cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking) != cudaSuccess) {
+    delete h;
+    return B2_ERR_CUDA;
+  }
+  h->own_stream = true;
+  h->log2_quirk_mask = compute_log2_quirk_mask();
+  *out = h;
+  return B2_OK;
+}
+
+extern "C" int b2_destroy(b2_handle h) {
+  if (!h) return B2_OK;
+  cudaSetDevice(h->device);
+  cudaStreamSynchronize(h->stream);
+  for (auto& w : h->ws)
+    if (w.p) cudaFree(w.p);
+  for (auto& p : h->pinned)
+    if (p.p) cudaFreeHost(p.p);
+  if (h->own_stream && h->stream) cudaStreamDestroy(h->stream);
+  delete h;
+  return B2_OK;
+}
+
+extern "C" int b2_set_stream(b2_handle h, void* s) {
+  if (!h) return B2_ERR_BAD_ARG;
+  cudaSetDevice(h->device);
+  if (h->own_stream && h->stream) {
+    cudaStreamSynchronize(h->stream);
+    cudaStreamDestroy(h->stream);
+  }
+  if (s) {
+    h->stream = (cudaStream_t)s;
+    h->own_stream = false;
+  } else {
+    B2_CUDA(h, cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
+    h->own_stream = true;
+  }
+  return B2_OK;
+}
+
+extern "C" int b2_synchronize(b2_handle h) {
+  if (!h) return B2_ERR_BAD_ARG;
+  B2_CUDA(h, cudaStreamSynchronize(h->stream));
+  return B2_OK;
+}
+
+extern "C" const char* b2_last_error(b2_handle h) { return h ? h->err.c_str() : "null handle"; }
+extern "C" int64_t b2_launch_count(b2_handle h) { return h ? h->launches : 0; }
+
+// ---- workspaces --------------------------------------------------------------------------
+int b2i_ws(b2_ctx* h, int which, size_t bytes, void** out) {
+  DeviceBuf& w = h->ws[which];
+  if (bytes > w.cap) {
+    // stream-ordered reuse: earlier kernels may still read the old block
+    B2_CUDA(h, cudaStreamSynchronize(h->stream));
+    if (w.p) B2_CUDA(h, cudaFree(w.p));
+    w.p = nullptr;
+    w.cap = 0;
+    size_t want = bytes + bytes / 8 + 256;
+    cudaError_t e = cudaMalloc(&w.p, want);
+    if (e != cudaSuccess) {
+      cudaGetLastError();
+      B2_FAIL(h, B2_ERR_NOMEM, "cudaMalloc(%zu) for workspace %d failed: %s", want, which,
+              cudaGetErrorString(e));
+    }
+    w.cap = want;
+  }
+  *out = w.p;
+  return B2_OK;
+}
+
+int b2i_pinned(b2_ctx* h, int which, size_t bytes, void** out) {
+  HostBuf& w = h->pinned[which];
+  if (bytes > w.cap) {
+    B2_CUDA(h, cudaStreamSynchronize(h->stream));
+    if (w.p) B2_CUDA(h, cudaFreeHost(w.p));
+    w.p = nullptr;
+    w.cap = 0;
+    size_t want = bytes + bytes / 8 + 256;
+    B2_CUDA(h, cudaMallocHost(&w.p, want));
+    w.cap = want;
+  }
+  *out = w.p;
+  return B2_OK;
+}
+
+// Metadata arena: host-side tables (offsets, per-job parameters) are packed into one pinned
+// block and uploaded with a single async copy per call.
+int b2i_meta_begin(b2_ctx* h, MetaArena* a, size_t bytes) {
+  a->h = h;
+  bytes = (bytes + 255) & ~size_t(255);
+  // The pinned block may still be the source of the previous call's async copy.
+  B2_CUDA(h, cudaStreamSynchronize(h->stream));
+  void *d, *p;
+  B2_TRY(b2i_ws(h, b2_ctx::WS_META, bytes, &d));
+  B2_TRY(b2i_pinned(h, 0, bytes, &p));
+  a->dbase = (char*)d;
+  a->hbase = (char*)p;
+  a->cap = bytes;
+  a->used = 0;
+  return B2_OK;
+}
+
+void* b2i_meta_reserve(MetaArena* a, size_t bytes, void** host_view) {
+  size_t at = (a->used + 15) & ~size_t(15);
+  if (at + bytes > a->cap) return nullptr;
+  a->used = at + bytes;
+  if (host_view) *host_view = a->hbase + at;
+  return a->dbase + at;
+}
+
+void* b2i_meta_put(MetaArena* a, const void* src, size_t bytes) {
+  void* hv;
+  void* d = b2i_meta_reserve(a, bytes, &hv);
+  if (d && bytes) memcpy(hv, src, bytes);
+  return d;
+}
+
+int b2i_meta_commit(MetaArena* a) {
+  b2_ctx* h = a->h;
+  if (a->used)
+    B2_CUDA(h, cudaMemcpyAsync(a->dbase, a->hbase, a->used, cudaMemcpyHostToDevice, h->stream));
+  return B2_OK;
+}
+
+// ---- helpers for B2_HOST calls -------------------------------------------------------------
+static int stage_in(b2_ctx* h, int which, const void* host, size_t bytes, void** dev) {
+  B2_TRY(b2i_ws(h, which, bytes ? bytes : 16, dev));
+  if (bytes)
+    B2_CUDA(h, cudaMemcpyAsync(*dev, host, bytes, cudaMemcpyHostToDevice, h->stream));
+  return B2_OK;
+}
+
+static int copy_out(b2_ctx* h, void* host, const void* dev, size_t bytes) {
+  if (bytes)
+    B2_CUDA(h, cudaMemcpyAsync(host, dev, bytes, cudaMemcpyDeviceToHost, h->stream));
+  return B2_OK;
+}
+
+#define B2_ENTER(h)                                   \
+  if (!(h)) return B2_ERR_BAD_ARG;                    \
+  (h)->err.clear();                                   \
+  if (cudaSetDevice((h)->device) != cudaSuccess) return B2_ERR_CUDA;
+
+// ---- VAD -----------------------------------------------------------------------------------
+extern "C" int b2_vad_frames_per_window(int frame_rate, int sample_rate) {
+  if (frame_rate <= 0 || sample_rate <= 0) return 0;
+  // speech_transformers.py:163-164: int(window_duration * frame_rate + 0.5)
+  return (int)((1.0 / (double)sample_rate) * (double)frame_rate + 0.5);
+}
+
+extern "C" int64_t b2_vad_num_windows(int64_t n_samples, int frame_rate, int sample_rate) {
+  int fpw = b2_vad_frames_per_window(frame_rate, sample_rate);
+  if (fpw <= 0 || n_samples < 0) return -1;
+  return (n_samples + fpw - 1) / fpw;  // len(range(0, n, fpw)), speech_transformers.py:169
+}
+
+extern "C" int b2_vad_energy_zcr(b2_handle h, const int16_t* pcm, const int64_t* pcm_off, int B,
+                                 int frame_rate, int sample_rate, float non_speech_label,
+                                 int64_t energy_threshold, int z_lo, int z_hi, float* out,
+                                 const int64_t* out_off, int memspace) {
+  B2_ENTER(h);
+  if (B < 0 || !pcm_off || !out_off) B2_FAIL(h, B2_ERR_BAD_ARG, "vad: null offset table / B<0");
+  int fpw = b2_vad_frames_per_window(frame_rate, sample_rate);
+  if (fpw <= 0) B2_FAIL(h, B2_ERR_BAD_ARG, "vad: bad frame_rate/sample_rate");
+  if (energy_threshold < 0) B2_FAIL(h, B2_ERR_BAD_ARG, "vad: negative energy threshold");
+  if (z_lo < 0) z_lo = 0;
+  if (z_hi < 0) z_hi = (3 * fpw) / 8;
+  for (int b = 0; b < B; ++b) {
+    int64_t n = pcm_off[b + 1] - pcm_off[b];
+    if (n < 0) B2_FAIL(h, B2_ERR_BAD_ARG, "vad: pcm_off not monotone at %d", b);
+    if (out_off[b + 1] - out_off[b] != (n + fpw - 1) / fpw)
+      B2_FAIL(h, B2_ERR_BAD_ARG, "vad: out_off[%d] span must be ceil(n/fpw)", b);
+  }
+  if (B == 0) return B2_OK;
+  int64_t n_total = pcm_off[B], w_total = out_off[B];
+  if ((n_total && !pcm) || (w_total && !out)) B2_FAIL(h, B2_ERR_BAD_ARG, "vad: null data pointer");
+  const int16_t* d_pcm = pcm;
+  float* d_out = out;
+  if (memspace == B2_HOST) {
+    void *dp, *dq;
+    B2_TRY(stage_in(h, b2_ctx::WS_STAGE_IN0, pcm, (size_t)n_total * 2, &dp));
+    B2_TRY(b2i_ws(h, b2_ctx::WS_STAGE_OUT, (size_t)w_total * 4 + 16, &dq));
+    d_pcm = (const int16_t*)dp;
+    d_out = (float*)dq;
+  }
+  B2_TRY(b2i_vad_launch(h, d_pcm, pcm_off, B, fpw, non_speech_label, energy_threshold, z_lo, z_hi,
+                        d_out, out_off));
+  if (memspace == B2_HOST) {
+    B2_TRY(copy_out(h, out, d_out, (size_t)w_total * 4));
+    B2_CUDA(h, cudaStreamSynchronize(h->stream));
+  }
+  return B2_OK;
+}
+
+extern "C" int b2_synth_pcm(b2_handle h, const uint8_t* window_class, int64_t n_windows, int fpw,
+                            uint32_t seed, int16_t* pcm_out, int memspace) {
+  B2_ENTER(h);
+  if (n_windows < 0 || fpw <= 0) B2_FAIL(h, B2_ERR_BAD_ARG, "synth: bad sizes");
+  if (n_windows == 0) return B2_OK;
+  if (!window_class || !pcm_out) B2_FAIL(h, B2_ERR_BAD_ARG, "synth: null pointer");
+  const uint8_t* d_cls = window_class;
+  int16_t* d_out = pcm_out;
+  size_t out_bytes = (size_t)n_windows * fpw * 2;
+  if (memspace == B2_HOST) {
+    void *dp, *dq;
+    B2_TRY(stage_in(h, b2_ctx::WS_STAGE_IN0, window_class, (size_t)n_windows, &dp));
+    B2_TRY(b2i_ws(h, b2_ctx::WS_STAGE_OUT, out_bytes, &dq));
+    d_cls = (const uint8_t*)dp;
+    d_out = (int16_t*)dq;
+  }
+  B2_TRY(b2i_synth_launch(h, d_cls, n_windows, fpw, seed, d_out));
+  if (memspace == B2_HOST) {
+    B2_TRY(copy_out(h, pcm_out, d_out, out_bytes));
+    B2_CUDA(h, cudaStreamSynchronize(h->stream));
+  }
+  return B2_OK;
+}
+
+// ---- rasteriser ----------------------------------------------------------------------------
+static double scaled_seconds_host(double t, double ratio) {
+  // timedelta(seconds=t*ratio).total_seconds(): see raster.cu (same arithmetic, host copy used
+  // only to size the output arrays).
+  volatile double x = t * ratio;
+  double whole;
+  double frac = modf(x, &whole);
+  volatile double fus = frac * 1e6;
+  long long us = (long long)whole * 1000000LL + (long long)nearbyint(fus);
+  return (double)us / 1e6;
+}
+
+extern "C" int b2_rasterize_lengths(const double* cue_end_s, const int64_t* cue_off, int B,
+                                    const double* ratios, int K, int per_pair_ratios,
+                                    int sample_rate, int64_t* lengths) {
+  if (B < 0 || K < 0 || !cue_off || (!ratios && K) || !lengths || sample_rate <= 0)
+    return B2_ERR_BAD_ARG;
+  for (int b = 0; b < B; ++b) {
+    // max over cues of scaled(end) == scaled(max end) for ratio > 0: the product, the microsecond
+    // rounding and the division are all monotone non-decreasing (speech_transformers.py:958-960)
+    double max_end = 0.0;
+    bool any = false;
+    for (int64_t c = cue_off[b]; c < cue_off[b + 1]; ++c)
+      if (!any || cue_end_s[c] > max_end) { max_end = cue_end_s[c]; any = true; }
+    for (int k = 0; k < K; ++k) {
+      double r = per_pair_ratios ? ratios[(size_t)b * K + k] : ratios[k];
+      if (!(r > 0.0)) return B2_ERR_BAD_ARG;
+      double max_time = 0.0;
+      if (any) {
+        double e = scaled_seconds_host(max_end, r);
+        if (e > max_time) max_time = e;
+      }
+      volatile double prod = max_time * (double)sample_rate;
+      lengths[(size_t)b * K + k] = (int64_t)prod + 2;  // speech_transformers.py:962
+    }
+  }
+  return B2_OK;
+}
+
+extern "C" int b2_rasterize(b2_handle h, const double* cue_start_s, const double* cue_end_s,
+                            const uint8_t* cue_keep, const int64_t* cue_off, int B,
+                            const double* ratios, int K, int per_pair_ratios,
+                            const double* levels, int sample_rate, double start_seconds,
+                            float* out, const int64_t* out_off, int memspace) {
+  B2_ENTER(h);
+  if (B < 0 || K < 0 || !cue_off || !out_off || sample_rate <= 0)
+    B2_FAIL(h, B2_ERR_BAD_ARG, "rasterize: bad arguments");
+  if (B == 0 || K == 0) return B2_OK;
+  if (!ratios || (cue_off[B] && (!cue_start_s || !cue_end_s)))
+    B2_FAIL(h, B2_ERR_BAD_ARG, "rasterize: null cue/ratio arrays");
+  int64_t total = out_off[(size_t)B * K];
+  if (total && !out) B2_FAIL(h, B2_ERR_BAD_ARG, "rasterize: null output");
+  float* d_out = out;
+  if (memspace == B2_HOST) {
+    void* dq;
+    B2_TRY(b2i_ws(h, b2_ctx::WS_STAGE_OUT, (size_t)total * 4 + 16, &dq));
+    d_out = (float*)dq;
+  }
+  B2_TRY(b2i_raster_launch(h, cue_start_s, cue_end_s, cue_keep, cue_off, B, ratios, K,
+                           per_pair_ratios, levels, sample_rate, start_seconds, d_out, out_off));
+  if (memspace == B2_HOST) {
+    B2_TRY(copy_out(h, out, d_out, (size_t)total * 4));
+    B2_CUDA(h, cudaStreamSynchronize(h->stream));
+  }
+  return B2_OK;
+}
+
+// ---- boundaries ----------------------------------------------------------------------------
+extern "C" int b2_first_last_nonzero(b2_handle h, const float* sig, const int64_t* sig_off, int n,
+                                     int64_t* first, int64_t* last, int memspace) {
+  B2_ENTER(h);
+  if (n < 0 || !sig_off || !first || !last) B2_FAIL(h, B2_ERR_BAD_ARG, "boundaries: bad arguments");
+  if (n == 0) return B2_OK;
+  const float* d_sig = sig;
+  int64_t *d_first = first, *d_last = last;
+  if (memspace == B2_HOST) {
+    void *dp, *dq;
+    B2_TRY(stage_in(h, b2_ctx::WS_STAGE_IN0, sig, (size_t)sig_off[n] * 4, &dp));
+    B2_TRY(b2i_ws(h, b2_ctx::WS_STAGE_OUT, (size_t)n * 16, &dq));
+    d_sig = (const float*)dp;
+    d_first = (int64_t*)dq;
+    d_last = d_first + n;
+  }
+  B2_TRY(b2i_bounds_launch(h, d_sig, sig_off, n, d_first, d_last));
+  if (memspace == B2_HOST) {
+    B2_TRY(copy_out(h, first, d_first, (size_t)n * 8));
+    B2_TRY(copy_out(h, last, d_last, (size_t)n * 8));
+    B2_CUDA(h, cudaStreamSynchronize(h->stream));
+  }
+  return B2_OK;
+}
+
+// ---- aligner -------------------------------------------------------------------------------
+extern "C" int b2_align_batch(b2_handle h, const float* ref, const int64_t* ref_off,
+                              const float* sub, const int64_t* sub_off, int B, int K,
+                              int32_t max_offset_samples, double* score, int32_t* offset,
+                              int32_t* status, int memspace) {
+  B2_ENTER(h);
+  if (B < 0 || K < 0 || !ref_off || !sub_off) B2_FAIL(h, B2_ERR_BAD_ARG, "align: bad arguments");
+  if (max_offset_samples < B2_MAX_OFFSET_NONE)
+    B2_FAIL(h, B2_ERR_BAD_ARG, "align: max_offset_samples must be >= 0 or B2_MAX_OFFSET_NONE");
+  if (B == 0 || K == 0) return B2_OK;
+  if (!score || !offset || !status) B2_FAIL(h, B2_ERR_BAD_ARG, "align: null output");
+  size_t J = (size_t)B * K;
+  const float *d_ref = ref, *d_sub = sub;
+  double* d_score = score;
+  int32_t *d_offset = offset, *d_status = status;
+  if (memspace == B2_HOST) {
+    void *dr, *ds, *dq;
+    B2_TRY(stage_in(h, b2_ctx::WS_STAGE_IN0, ref, (size_t)ref_off[B] * 4, &dr));
+    B2_TRY(stage_in(h, b2_ctx::WS_STAGE_IN1, sub, (size_t)sub_off[J] * 4, &ds));
+    B2_TRY(b2i_ws(h, b2_ctx::WS_STAGE_OUT, J * 16 + 64, &dq));
+    d_ref = (const float*)dr;
+    d_sub = (const float*)ds;
+    d_score = (double*)dq;
+    d_offset = (int32_t*)(d_score + J);
+    d_status = d_offset + J;
+  }
+  B2_TRY(b2i_align_launch(h, d_ref, ref_off, d_sub, sub_off, B, K, max_offset_samples, d_score,
+                          d_offset, d_status));
+  if (memspace == B2_HOST) {
+    B2_TRY(copy_out(h, score, d_score, J * 8));
+    B2_TRY(copy_out(h, offset, d_offset, J * 4));
+    B2_TRY(copy_out(h, status, d_status, J * 4));
+    B2_CUDA(h, cudaStreamSynchronize(h->stream));
+  }
+  return B2_OK;
+}
+
+extern "C" int b2_reduce_ratios(b2_handle h, const double* score, const int32_t* offset,
+                                const int32_t* status, int B, int K, int32_t max_offset_samples,
+                                double* best_score, int32_t* best_offset, int32_t* best_k,
+                                int memspace) {
+  B2_ENTER(h);
+  if (B < 0 || K <= 0) B2_FAIL(h, B2_ERR_BAD_ARG, "reduce: bad arguments");
+  if (B == 0) return B2_OK;
+  if (!score || !offset || !best_score || !best_offset || !best_k)
+    B2_FAIL(h, B2_ERR_BAD_ARG, "reduce: null pointer");
+  size_t J = (size_t)B * K;
+  const double* d_score = score;
+  const int32_t *d_offset = offset, *d_status = status;
+  double* d_bs = best_score;
+  int32_t *d_bo = best_offset, *d_bk = best_k;
+  if (memspace == B2_HOST) {
+    void *d0, *dq;
+    B2_TRY(b2i_ws(h, b2_ctx::WS_STAGE_IN0, J * 16 + 64, &d0));
+    B2_CUDA(h, cudaMemcpyAsync(d0, score, J * 8, cudaMemcpyHostToDevice, h->stream));
+    int32_t* doff = (int32_t*)((char*)d0 + J * 8);
+    B2_CUDA(h, cudaMemcpyAsync(doff, offset, J * 4, cudaMemcpyHostToDevice, h->stream));
+    int32_t* dst = doff + J;
+    if (status)
+      B2_CUDA(h, cudaMemcpyAsync(dst, status, J * 4, cudaMemcpyHostToDevice, h->stream));
+    B2_TRY(b2i_ws(h, b2_ctx::WS_STAGE_OUT, (size_t)B * 16 + 64, &dq));
+    d_score = (const double*)d0;
+    d_offset = doff;
+    d_status = status ? dst : nullptr;
+    d_bs = (double*)dq;
+    d_bo = (int32_t*)(d_bs + B);
+    d_bk = d_bo + B;
+  }
+  B2_TRY(b2i_reduce_launch(h, d_score, d_offset, d_status, B, K, max_offset_samples, d_bs, d_bo,
+                           d_bk));
+  if (memspace == B2_HOST) {
+    B2_TRY(copy_out(h, best_score, d_bs, (size_t)B * 8));
+    B2_TRY(copy_out(h, best_offset, d_bo, (size_t)B * 4));
+    B2_TRY(copy_out(h, best_k, d_bk, (size_t)B * 4));
+    B2_CUDA(h, cudaStreamSynchronize(h->stream));
+  }
+  return B2_OK;
+}
+
+// ---- whole hot path --------------------------------------------------------------------------
+// VideoSpeechTransformer.fit (VAD) -> K x (SubtitleScaler + SubtitleSpeechTransformer) ->
+// MaxScoreAligner(FFTAligner).fit_transform, for B pairs (ffsubsync/ffsubsync.py:637,196-235).
+extern "C" int b2_sync_batch(b2_handle h, const int16_t* pcm, const int64_t* pcm_off, int B,
+                             int frame_rate, int sample_rate, float non_speech_label,
+                             int64_t energy_threshold, int z_lo, int z_hi,
+                             const double* cue_start_s, const double* cue_end_s,
+                             const uint8_t* cue_keep, const int64_t* cue_off, const double* ratios,
+                             int K, double start_seconds, int32_t max_offset_samples,
+                             double* best_score, int32_t* best_offset, int32_t* best_k,
+                             double* all_score, int32_t* all_offset, int memspace) {
+  B2_ENTER(h);
+  if (B < 0 || K <= 0 || !pcm_off || !cue_off || !ratios)
+    B2_FAIL(h, B2_ERR_BAD_ARG, "sync_batch: bad arguments");
+  if (B == 0) return B2_OK;
+  if (!best_score || !best_offset || !best_k) B2_FAIL(h, B2_ERR_BAD_ARG, "sync_batch: null output");
+  const int fpw = b2_vad_frames_per_window(frame_rate, sample_rate);
+  if (fpw <= 0) B2_FAIL(h, B2_ERR_BAD_ARG, "sync_batch: bad frame_rate/sample_rate");
+  if (z_lo < 0) z_lo = 0;
+  if (z_hi < 0) z_hi = (3 * fpw) / 8;
+  const size_t J = (size_t)B * K;
+  std::vector<int64_t> ref_off(B + 1), sub_off(J + 1), lengths(J);
+  ref_off[0] = 0;
+  for (int b = 0; b < B; ++b) {
+    const int64_t n = pcm_off[b + 1] - pcm_off[b];
+    if (n < 0) B2_FAIL(h, B2_ERR_BAD_ARG, "sync_batch: pcm_off not monotone");
+    ref_off[b + 1] = ref_off[b] + (n + fpw - 1) / fpw;
+  }
+  if (b2_rasterize_lengths(cue_end_s, cue_off, B, ratios, K, 0, sample_rate, lengths.data()) != B2_OK)
+    B2_FAIL(h, B2_ERR_BAD_ARG, "sync_batch: bad cue list / ratios");
+  sub_off[0] = 0;
+  for (size_t j = 0; j < J; ++j) sub_off[j + 1] = sub_off[j] + lengths[j];
+
+  void *d_refsig, *d_subsig, *d_res;
+  B2_TRY(b2i_ws(h, b2_ctx::WS_SIG_REF, (size_t)ref_off[B] * 4 + 64, &d_refsig));
+  B2_TRY(b2i_ws(h, b2_ctx::WS_SIG_SUB, (size_t)sub_off[J] * 4 + 64, &d_subsig));
+  B2_TRY(b2i_ws(h, b2_ctx::WS_MISC, J * 16 + (size_t)B * 16 + 256, &d_res));
+  double* d_score = (double*)d_res;
+  double* d_bs = d_score + J;
+  int32_t* d_offset = (int32_t*)(d_bs + B);
+  int32_t* d_status = d_offset + J;
+  int32_t* d_bo = d_status + J;
+  int32_t* d_bk = d_bo + B;
+
+  const int16_t* d_pcm = pcm;
+  if (memspace == B2_HOST) {
+    void* dp;
+    B2_TRY(stage_in(h, b2_ctx::WS_STAGE_IN0, pcm, (size_t)pcm_off[B] * 2, &dp));
+    d_pcm = (const int16_t*)dp;
+  }
+  B2_TRY(b2i_vad_launch(h, d_pcm, pcm_off, B, fpw, non_speech_label, energy_threshold, z_lo, z_hi,
+                        (float*)d_refsig, ref_off.data()));
+  B2_TRY(b2i_raster_launch(h, cue_start_s, cue_end_s, cue_keep, cue_off, B, ratios, K, 0, nullptr,
+                           sample_rate, start_seconds, (float*)d_subsig, sub_off.data()));
+  double* o_score = (memspace == B2_DEVICE && all_score) ? all_score : d_score;
+  int32_t* o_offset = (memspace == B2_DEVICE && all_offset) ? all_offset : d_offset;
+  B2_TRY(b2i_align_launch(h, (const float*)d_refsig, ref_off.data(), (const float*)d_subsig,
+                          sub_off.data(), B, K, max_offset_samples, o_score, o_offset, d_status));
+  if (memspace == B2_DEVICE) {
+    B2_TRY(b2i_reduce_launch(h, o_score, o_offset, d_status, B, K, max_offset_samples, best_score,
+                             best_offset, best_k));
+    return B2_OK;
+  }
+  B2_TRY(b2i_reduce_launch(h, o_score, o_offset, d_status, B, K, max_offset_samples, d_bs, d_bo, d_bk));
+  B2_TRY(copy_out(h, best_score, d_bs, (size_t)B * 8));
+  B2_TRY(copy_out(h, best_offset, d_bo, (size_t)B * 4));
+  B2_TRY(copy_out(h, best_k, d_bk, (size_t)B * 4));
+  if (all_score) B2_TRY(copy_out(h, all_score, d_score, J * 8));
+  if (all_offset) B2_TRY(copy_out(h, all_offset, d_offset, J * 4));
+  B2_CUDA(h, cudaStreamSynchronize(h->stream));
+  return B2_OK;
+}

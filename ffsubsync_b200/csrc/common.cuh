@@ -1,0 +1,104 @@
+// Shared plumbing for the B200 ffsubsync hot-path library (internal; the ABI is
+// include/ffsubsync_b200.h).  sm_100a only.
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <string>
+#include <vector>
+
+#include "../../include/ffsubsync_b200.h"
+
+struct DeviceBuf {
+  void* p = nullptr;
+  size_t cap = 0;
+};
+
+struct HostBuf {  // pinned
+  void* p = nullptr;
+  size_t cap = 0;
+};
+
+struct b2_ctx {
+  int device = 0;
+  int sm_count = 148;
+  cudaStream_t stream = nullptr;
+  bool own_stream = true;
+  std::string err;
+  int64_t launches = 0;
+  uint64_t log2_quirk_mask = 0;  // bit k set: CPython's ceil(math.log(2**k, 2)) == k + 1
+  // named grow-only workspaces
+  enum { WS_STAGE_IN0, WS_STAGE_IN1, WS_STAGE_OUT, WS_META, WS_SPEC, WS_SCORES, WS_CAND,
+         WS_SIG_REF, WS_SIG_SUB, WS_MISC, WS_COUNT };
+  DeviceBuf ws[WS_COUNT];
+  HostBuf pinned[4];
+};
+
+#define B2_FAIL(h, code, ...)                          \
+  do {                                                 \
+    char _b[512];                                      \
+    snprintf(_b, sizeof(_b), __VA_ARGS__);             \
+    (h)->err = _b;                                     \
+    return (code);                                     \
+  } while (0)
+
+#define B2_CUDA(h, expr)                                                              \
+  do {                                                                                \
+    cudaError_t _e = (expr);                                                          \
+    if (_e != cudaSuccess)                                                            \
+      B2_FAIL(h, B2_ERR_CUDA, "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e), \
+              __FILE__, __LINE__);                                                    \
+  } while (0)
+
+#define B2_CHECK_LAUNCH(h, name)                                                         \
+  do {                                                                                   \
+    (h)->launches++;                                                                     \
+    cudaError_t _e = cudaGetLastError();                                                 \
+    if (_e != cudaSuccess)                                                               \
+      B2_FAIL(h, B2_ERR_CUDA, "launch of %s failed: %s", name, cudaGetErrorString(_e));  \
+  } while (0)
+
+#define B2_TRY(expr)            \
+  do {                          \
+    int _s = (expr);            \
+    if (_s != B2_OK) return _s; \
+  } while (0)
+
+int b2i_ws(b2_ctx* h, int which, size_t bytes, void** out);
+int b2i_pinned(b2_ctx* h, int which, size_t bytes, void** out);
+// Upload a small host array into the META workspace region (async on h->stream).
+struct MetaArena {
+  b2_ctx* h;
+  char* dbase = nullptr;
+  char* hbase = nullptr;
+  size_t cap = 0, used = 0;
+};
+int b2i_meta_begin(b2_ctx* h, MetaArena* a, size_t bytes);
+void* b2i_meta_put(MetaArena* a, const void* src, size_t bytes);  // returns device pointer
+void* b2i_meta_reserve(MetaArena* a, size_t bytes, void** host_view);
+int b2i_meta_commit(MetaArena* a);
+
+static inline int64_t ceil_div64(int64_t a, int64_t b) { return (a + b - 1) / b; }
+
+// ---- kernels' host launchers (defined in the .cu files) ------------------------------------
+int b2i_vad_launch(b2_ctx* h, const int16_t* d_pcm, const int64_t* pcm_off_host, int B, int fpw,
+                   float non_speech_label, int64_t energy_threshold, int z_lo, int z_hi,
+                   float* d_out, const int64_t* out_off_host);
+int b2i_synth_launch(b2_ctx* h, const uint8_t* d_cls, int64_t n_windows, int fpw, uint32_t seed,
+                     int16_t* d_out);
+int b2i_raster_launch(b2_ctx* h, const double* cue_start, const double* cue_end,
+                      const uint8_t* cue_keep, const int64_t* cue_off, int B, const double* ratios,
+                      int K, int per_pair_ratios, const double* levels, int sample_rate,
+                      double start_seconds, float* d_out, const int64_t* out_off_host);
+int b2i_bounds_launch(b2_ctx* h, const float* d_sig, const int64_t* off_host, int n,
+                      int64_t* d_first, int64_t* d_last);
+int b2i_align_launch(b2_ctx* h, const float* d_ref, const int64_t* ref_off_host,
+                     const float* d_sub, const int64_t* sub_off_host, int B, int K,
+                     int32_t max_offset_samples, double* d_score, int32_t* d_offset,
+                     int32_t* d_status);
+int b2i_reduce_launch(b2_ctx* h, const double* d_score, const int32_t* d_offset,
+                      const int32_t* d_status, int B, int K, int32_t max_offset_samples,
+                      double* d_best_score, int32_t* d_best_offset, int32_t* d_best_k);

@@ -1,0 +1,475 @@
+// K3-K5: batched cross-correlation of reference / subtitle speech signals over a window of
+// candidate offsets, + exact re-scoring and argmax.  Replaces FFTAligner.fit
+// (ffsubsync/aligners.py:50-80, mask :31-43, argmax :45-48).
+//
+// What the reference computes, in closed form:
+//     score(o) = sum_j s'[j] * r'[j + o],   x' = 2x - 1,  terms outside either signal = 0
+// for the offsets o = N-1-idx-S that survive the max_offset mask, and returns the maximum
+// (first index = largest offset among equals).
+//
+// How it is computed here.  Only a window [o_lo, o_hi] of offsets is wanted (12 000 of them for
+// the default --max-offset-seconds 60), so the subtitle signal is cut into blocks of
+// L = P - W + 1 samples; each block and the P reference samples it can meet are transformed with
+// a P = 2^15 point real FFT that lives entirely in shared memory, conj(A)*B is accumulated over
+// the blocks in registers, and ONE inverse transform yields the W scores (overlap-save
+// correlation).  The reference-side spectra are computed once per pair and reused by all K
+// ratio candidates.  The fp32 scores only nominate candidates: every offset within a proven
+// round-off bound of the maximum is re-scored exactly (float64 direct sum), so the returned
+// offset and score do not depend on FFT round-off.  Offset ranges wider than P/2 are tiled.
+#include <math.h>
+
+#include <algorithm>
+
+#include "common.cuh"
+#include "corr.cuh"
+
+namespace {
+
+using namespace corr;
+
+constexpr int kCandMax = 32;
+// candidates within kTauRel * sqrt(Es*Er) of the fp32 maximum are re-scored exactly; measured
+// round-off of the chain is < 6 * 2^-24 * sqrt(Es*Er) (tests/test_corr_emul.py, tests/test_gpu_align.py)
+constexpr float kTauRel = 64.0f * 5.9604645e-8f;
+
+struct SpecItem {      // one reference block to transform
+  long long ref_off;   // element offset of the pair's reference signal
+  int R;
+  int i0;              // reference index of sample 0 of the block (may be negative)
+};
+
+struct SubJob {        // one (pair, ratio, offset tile)
+  long long sub_off;
+  long long score_off; // where the tile's Wt scores go
+  long long spec_base; // index of the spectrum of block blk_lo
+  int S, blk_lo, blk_hi, n_out, energy_slot;
+};
+
+struct SelJob {        // one (pair, ratio)
+  long long ref_off, sub_off, score_off;
+  int R, S, o_first;   // offset of scores[score_off]
+  int m_lo, m_hi;      // valid window of m (inclusive); m_lo > m_hi: nothing survives
+  int energy_slot, n_tiles;
+  int out_index;       // b*K + k
+  int kind;            // 0 normal, 1 empty input, 2 everything masked
+  int masked_offset;   // offset reported when kind == 2
+};
+
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kThreads, 1)
+    ref_spectra_kernel(const float* __restrict__ ref, const SpecItem* __restrict__ items,
+                       float4* __restrict__ spec, float* __restrict__ spec_energy) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  float2* buf = reinterpret_cast<float2*>(smem_raw);
+  float2* tw1024 = buf + kM;
+  float2* fine32 = tw1024 + 1024;
+  __shared__ float red[kThreads / 32];
+  const int tid = threadIdx.x;
+  const SpecItem it = items[blockIdx.x];
+  init_tables(tw1024, fine32, tid);
+  __syncthreads();
+  const Tables t{tw1024, fine32};
+  BlockSource s;
+  s.src = ref + it.ref_off + it.i0;
+  s.t_lo = it.i0 < 0 ? -it.i0 : 0;
+  s.t_hi = min(it.R - it.i0, kP);
+  float ss = forward_block(buf, t, tid, s);
+  spec_store(buf, t, tid, spec + (size_t)blockIdx.x * kPairs);
+  for (int o = 16; o > 0; o >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o);
+  if ((tid & 31) == 0) red[tid >> 5] = ss;
+  __syncthreads();
+  if (tid == 0) {
+    float e = 0.f;
+    for (int w = 0; w < kThreads / 32; ++w) e += red[w];
+    spec_energy[blockIdx.x] = e;
+  }
+}
+
+__global__ void __launch_bounds__(kThreads, 1)
+    sub_correlate_kernel(const float* __restrict__ sub, const SubJob* __restrict__ jobs,
+                         const float4* __restrict__ spec, const float* __restrict__ spec_energy,
+                         int L, float* __restrict__ scores, float2* __restrict__ job_energy) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  float2* buf = reinterpret_cast<float2*>(smem_raw);
+  float2* tw1024 = buf + kM;
+  float2* fine32 = tw1024 + 1024;
+  __shared__ float red[kThreads / 32];
+  const int tid = threadIdx.x;
+  const SubJob job = jobs[blockIdx.x];
+  float* out = scores + job.score_off;
+  if (job.blk_lo >= job.blk_hi) {  // no subtitle block meets the reference at these offsets
+    for (int m = tid; m < job.n_out; m += kThreads) out[m] = 0.f;
+    if (tid == 0) job_energy[job.energy_slot] = make_float2(0.f, 0.f);
+    return;
+  }
+  init_tables(tw1024, fine32, tid);
+  __syncthreads();
+  const Tables t{tw1024, fine32};
+  SubState st;
+  sub_state_clear(st);
+  float er = 0.f;
+  for (int blk = job.blk_lo; blk < job.blk_hi; ++blk) {
+    const int j0 = blk * L;
+    BlockSource s;
+    s.src = sub + job.sub_off + j0;
+    s.t_lo = 0;
+    s.t_hi = min(job.S - j0, L);
+    st.ss += forward_block(buf, t, tid, s);
+    const size_t item = (size_t)(job.spec_base + (blk - job.blk_lo));
+    sub_accumulate(st, buf, t, tid, spec + item * kPairs);
+    er += spec_energy[item];
+    __syncthreads();  // buf is rewritten by the next block's first pass
+  }
+  sub_retangle_store(st, buf, t, tid);
+  __syncthreads();
+  inverse_passes_1(buf, tid);
+  __syncthreads();
+  inverse_passes_2(buf, t, tid);
+  __syncthreads();
+  inverse_passes_3(buf, t, tid);
+  __syncthreads();
+  inverse_passes_4(buf, t, tid);
+  __syncthreads();
+  for (int m = tid; m < job.n_out; m += kThreads) out[m] = window_value(buf, m);
+  float ss = st.ss;
+  for (int o = 16; o > 0; o >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o);
+  if ((tid & 31) == 0) red[tid >> 5] = ss;
+  __syncthreads();
+  if (tid == 0) {
+    float e = 0.f;
+    for (int w = 0; w < kThreads / 32; ++w) e += red[w];
+    job_energy[job.energy_slot] = make_float2(e, er);
+  }
+}
+
+// ---- candidate selection ---------------------------------------------------------------------
+// Per (pair, ratio): approximate maximum over the surviving window, then every offset whose
+// fp32 score is within tau of it, taken from the LARGEST offset down (np.argmax returns the
+// lowest index = largest offset among equal values), at most kCandMax of them.
+__global__ void __launch_bounds__(256) select_candidates_kernel(
+    const SelJob* __restrict__ jobs, const float* __restrict__ scores,
+    const float2* __restrict__ job_energy, int* __restrict__ cand_off,
+    int* __restrict__ cand_cnt) {
+  const SelJob job = jobs[blockIdx.x];
+  const int tid = threadIdx.x;
+  __shared__ float smax[256];
+  __shared__ int scount;
+  __shared__ int swarp[8];
+  if (job.kind != 0 || job.m_lo > job.m_hi) {
+    if (tid == 0) cand_cnt[blockIdx.x] = 0;
+    return;
+  }
+  const float* c = scores + job.score_off;
+  float mx = -INFINITY;
+  for (int m = job.m_lo + tid; m <= job.m_hi; m += 256) mx = fmaxf(mx, c[m]);
+  smax[tid] = mx;
+  __syncthreads();
+  for (int w = 128; w > 0; w >>= 1) {
+    if (tid < w) smax[tid] = fmaxf(smax[tid], smax[tid + w]);
+    __syncthreads();
+  }
+  mx = smax[0];
+  float e2 = 0.f;
+  for (int i = 0; i < job.n_tiles; ++i) {
+    const float2 e = job_energy[job.energy_slot + i];
+    e2 = fmaxf(e2, e.x * e.y);
+  }
+  const float cut = mx - (kTauRel * sqrtf(e2) + 1e-30f);
+  if (tid == 0) scount = 0;
+  __syncthreads();
+  // walk m from high to low so that slots fill in order of increasing index m_hi - m ... wait:
+  // offset o = o_first + m, so the largest offset is the largest m.
+  for (int top = job.m_hi; top >= job.m_lo; top -= 256) {
+    const int m = top - tid;
+    const bool hit = (m >= job.m_lo) && (c[m] >= cut);
+    const unsigned ball = __ballot_sync(0xffffffffu, hit);
+    if ((tid & 31) == 0) swarp[tid >> 5] = __popc(ball);
+    __syncthreads();
+    int before = scount;
+    for (int w = 0; w < (tid >> 5); ++w) before += swarp[w];
+    before += __popc(ball & ((1u << (tid & 31)) - 1u));
+    if (hit && before < kCandMax) cand_off[(size_t)blockIdx.x * kCandMax + before] = job.o_first + m;
+    __syncthreads();
+    if (tid == 0) {
+      int tot = 0;
+      for (int w = 0; w < 8; ++w) tot += swarp[w];
+      scount += tot;
+    }
+    __syncthreads();
+  }
+  if (tid == 0) cand_cnt[blockIdx.x] = scount;
+}
+
+// ---- exact re-score ----------------------------------------------------------------------------
+// score(o) = sum over the overlap of (2 s[j] - 1)(2 r[j+o] - 1), float64, fixed summation order.
+__global__ void __launch_bounds__(256) rescore_kernel(const SelJob* __restrict__ jobs,
+                                                       const float* __restrict__ ref,
+                                                       const float* __restrict__ sub,
+                                                       const int* __restrict__ cand_off,
+                                                       const int* __restrict__ cand_cnt,
+                                                       double* __restrict__ cand_score) {
+  const int j = blockIdx.y, ci = blockIdx.x;
+  const int n = min(cand_cnt[j], kCandMax);
+  if (ci >= n) return;
+  const SelJob job = jobs[j];
+  const int o = cand_off[(size_t)j * kCandMax + ci];
+  const float* r = ref + job.ref_off;
+  const float* s = sub + job.sub_off;
+  const int j_lo = max(0, -o), j_hi = min(job.S, job.R - o);
+  double acc = 0.0;
+  for (int i = j_lo + threadIdx.x; i < j_hi; i += 256) {
+    const double a = 2.0 * (double)__ldg(s + i) - 1.0;
+    const double b = 2.0 * (double)__ldg(r + i + o) - 1.0;
+    acc = fma(a, b, acc);
+  }
+  __shared__ double sh[256];
+  sh[threadIdx.x] = acc;
+  __syncthreads();
+  for (int w = 128; w > 0; w >>= 1) {
+    if (threadIdx.x < w) sh[threadIdx.x] += sh[threadIdx.x + w];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) cand_score[(size_t)j * kCandMax + ci] = sh[0];
+}
+
+__global__ void __launch_bounds__(128) pick_kernel(const SelJob* __restrict__ jobs, int n_jobs,
+                                                    const int* __restrict__ cand_off,
+                                                    const int* __restrict__ cand_cnt,
+                                                    const double* __restrict__ cand_score,
+                                                    double* __restrict__ score,
+                                                    int32_t* __restrict__ offset,
+                                                    int32_t* __restrict__ status) {
+  const int j = blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= n_jobs) return;
+  const SelJob job = jobs[j];
+  if (job.kind == 1) {
+    score[job.out_index] = 0.0;
+    offset[job.out_index] = 0;
+    status[job.out_index] = B2_ALIGN_EMPTY;
+    return;
+  }
+  if (job.kind == 2 || job.m_lo > job.m_hi) {
+    score[job.out_index] = -INFINITY;  // np.argmax of an all -inf array: index 0
+    offset[job.out_index] = job.masked_offset;
+    status[job.out_index] = B2_ALIGN_ALL_MASKED;
+    return;
+  }
+  const int cnt = cand_cnt[j];
+  const int n = min(cnt, kCandMax);
+  double bs = -INFINITY;
+  int bo = 0;
+  for (int c = 0; c < n; ++c) {
+    const double s = cand_score[(size_t)j * kCandMax + c];
+    const int o = cand_off[(size_t)j * kCandMax + c];
+    if (c == 0 || s > bs || (s == bs && o > bo)) {
+      bs = s;
+      bo = o;
+    }
+  }
+  score[job.out_index] = bs;
+  offset[job.out_index] = bo;
+  status[job.out_index] = cnt > kCandMax ? B2_ALIGN_CAND_OVERFLOW : B2_ALIGN_OK;
+}
+
+// ---- host planning ----------------------------------------------------------------------------
+long long padded_length(const b2_ctx* h, long long n) {
+  // int(2 ** math.ceil(math.log(n, 2))), aligners.py:67-68, libm quirks included
+  int k = 0;
+  while ((1LL << k) < n) ++k;
+  if ((1LL << k) == n && (h->log2_quirk_mask >> k) & 1ULL) ++k;
+  return 1LL << k;
+}
+
+long long floor_div(long long a, long long b) {
+  long long q = a / b;
+  if ((a % b != 0) && ((a < 0) != (b < 0))) --q;
+  return q;
+}
+
+}  // namespace
+
+int b2i_align_launch(b2_ctx* h, const float* d_ref, const int64_t* ref_off, const float* d_sub,
+                     const int64_t* sub_off, int B, int K, int32_t max_offset_samples,
+                     double* d_score, int32_t* d_offset, int32_t* d_status) {
+  const size_t J = (size_t)B * K;
+  std::vector<SelJob> sel(J);
+  struct PairPlan { long long o_min, o_max; int n_tiles; bool any; };
+  std::vector<PairPlan> pp(B);
+  long long max_w = 1;
+  for (int b = 0; b < B; ++b) {
+    const long long R = ref_off[b + 1] - ref_off[b];
+    if (R < 0 || R > 0x3fffffff) B2_FAIL(h, B2_ERR_BAD_ARG, "align: bad reference length at %d", b);
+    PairPlan& p = pp[b];
+    p.any = false;
+    p.o_min = 0;
+    p.o_max = -1;
+    for (int k = 0; k < K; ++k) {
+      const size_t j = (size_t)b * K + k;
+      const long long S = sub_off[j + 1] - sub_off[j];
+      if (S < 0 || S > 0x3fffffff) B2_FAIL(h, B2_ERR_BAD_ARG, "align: bad subtitle length at %zu", j);
+      SelJob& s = sel[j];
+      memset(&s, 0, sizeof(s));
+      s.ref_off = ref_off[b];
+      s.sub_off = sub_off[j];
+      s.R = (int)R;
+      s.S = (int)S;
+      s.out_index = (int)j;
+      if (R == 0 || S == 0) {  // aligners.py:58-66
+        s.kind = 1;
+        continue;
+      }
+      const long long N = padded_length(h, R + S);
+      long long lo = 0, hi = N;  // surviving index range, aligners.py:31-43 with slice semantics
+      if (max_offset_samples >= 0) {
+        const long long a = N - 1 - max_offset_samples - S;
+        const long long bb = N - 1 + (long long)max_offset_samples - S;
+        lo = a >= 0 ? std::min(a, N) : std::max(a + N, 0LL);
+        hi = bb >= 0 ? std::min(bb, N) : std::max(bb + N, 0LL);
+      }
+      if (lo >= hi) {
+        s.kind = 2;
+        s.masked_offset = (int)(N - 1 - S);
+        continue;
+      }
+      const long long o_lo = N - S - hi, o_hi = N - 1 - S - lo;  // aligners.py:47
+      s.kind = 0;
+      s.m_lo = (int)o_lo;  // temporarily absolute offsets; rebased below
+      s.m_hi = (int)o_hi;
+      if (!p.any) {
+        p.o_min = o_lo;
+        p.o_max = o_hi;
+        p.any = true;
+      } else {
+        p.o_min = std::min(p.o_min, o_lo);
+        p.o_max = std::max(p.o_max, o_hi);
+      }
+    }
+    if (p.any) max_w = std::max(max_w, p.o_max - p.o_min + 1);
+  }
+  const int Wt = (int)(max_w <= kP / 2 + 1 ? (max_w | 1) : (kP / 2 + 1));
+  const int L = kP - Wt + 1;
+
+  // score buffers + per-(pair,ratio) bookkeeping
+  long long score_total = 0, energy_total = 0;
+  for (int b = 0; b < B; ++b) {
+    PairPlan& p = pp[b];
+    p.n_tiles = p.any ? (int)ceil_div64(p.o_max - p.o_min + 1, Wt) : 0;
+    for (int k = 0; k < K; ++k) {
+      SelJob& s = sel[(size_t)b * K + k];
+      if (s.kind != 0) continue;
+      s.o_first = (int)p.o_min;
+      s.m_lo -= (int)p.o_min;
+      s.m_hi -= (int)p.o_min;
+      s.score_off = score_total;
+      s.energy_slot = (int)energy_total;
+      s.n_tiles = p.n_tiles;
+      score_total += (long long)p.n_tiles * Wt;
+      energy_total += p.n_tiles;
+    }
+  }
+
+  void *d_scores, *d_cand;
+  B2_TRY(b2i_ws(h, b2_ctx::WS_SCORES, (size_t)(score_total + 16) * 4 + (size_t)(energy_total + 1) * 8,
+                &d_scores));
+  float* scores = (float*)d_scores;
+  float2* job_energy = (float2*)((char*)d_scores + (((size_t)(score_total + 16) * 4 + 7) & ~size_t(7)));
+  B2_TRY(b2i_ws(h, b2_ctx::WS_CAND, J * kCandMax * 12 + J * 4 + 64, &d_cand));
+  double* cand_score = (double*)d_cand;
+  int* cand_off = (int*)(cand_score + J * kCandMax);
+  int* cand_cnt = cand_off + J * kCandMax;
+
+  B2_CUDA(h, cudaFuncSetAttribute(ref_spectra_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  (int)kSmemBytes));
+  B2_CUDA(h, cudaFuncSetAttribute(sub_correlate_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  (int)kSmemBytes));
+
+  // Work is issued in groups so that the reference spectra of a group fit the workspace cap.
+  const size_t kSpecBytes = (size_t)kPairs * 16;
+  const size_t cap_items = std::max<size_t>(64, ((size_t)6 << 30) / kSpecBytes);
+  std::vector<SpecItem> items;
+  std::vector<SubJob> jobs;
+  auto flush = [&]() -> int {
+    if (jobs.empty()) {
+      items.clear();
+      return B2_OK;
+    }
+    void* d_spec;
+    B2_TRY(b2i_ws(h, b2_ctx::WS_SPEC, items.size() * kSpecBytes + items.size() * 4 + 256, &d_spec));
+    float4* spec = (float4*)d_spec;
+    float* spec_energy = (float*)((char*)d_spec + items.size() * kSpecBytes);
+    MetaArena a;
+    B2_TRY(b2i_meta_begin(h, &a, items.size() * sizeof(SpecItem) + jobs.size() * sizeof(SubJob) + 256));
+    const SpecItem* d_items = (const SpecItem*)b2i_meta_put(&a, items.data(), items.size() * sizeof(SpecItem));
+    const SubJob* d_jobs = (const SubJob*)b2i_meta_put(&a, jobs.data(), jobs.size() * sizeof(SubJob));
+    B2_TRY(b2i_meta_commit(&a));
+    if (!items.empty()) {
+      ref_spectra_kernel<<<(unsigned)items.size(), kThreads, kSmemBytes, h->stream>>>(
+          d_ref, d_items, spec, spec_energy);
+      B2_CHECK_LAUNCH(h, "ref_spectra_kernel");
+    }
+    sub_correlate_kernel<<<(unsigned)jobs.size(), kThreads, kSmemBytes, h->stream>>>(
+        d_sub, d_jobs, spec, spec_energy, L, scores, job_energy);
+    B2_CHECK_LAUNCH(h, "sub_correlate_kernel");
+    items.clear();
+    jobs.clear();
+    return B2_OK;
+  };
+
+  for (int b = 0; b < B; ++b) {
+    const PairPlan& p = pp[b];
+    if (!p.any) continue;
+    const long long R = ref_off[b + 1] - ref_off[b];
+    long long nblk_max = 0;
+    for (int k = 0; k < K; ++k) {
+      const SelJob& s = sel[(size_t)b * K + k];
+      if (s.kind == 0) nblk_max = std::max<long long>(nblk_max, ceil_div64(s.S, L));
+    }
+    for (int tile = 0; tile < p.n_tiles; ++tile) {
+      const long long o_t = p.o_min + (long long)tile * Wt;
+      const long long blk_lo = std::max(0LL, floor_div(-o_t - kP, L) + 1);
+      const long long blk_hi = std::min<long long>(nblk_max, R - o_t > 0 ? ceil_div64(R - o_t, L) : 0LL);
+      const long long n_items = std::max(0LL, blk_hi - blk_lo);
+      if (items.size() + (size_t)n_items > cap_items) B2_TRY(flush());
+      const long long spec_base = (long long)items.size();
+      for (long long blk = blk_lo; blk < blk_hi; ++blk) {
+        SpecItem it;
+        it.ref_off = ref_off[b];
+        it.R = (int)R;
+        it.i0 = (int)(blk * L + o_t);
+        items.push_back(it);
+      }
+      for (int k = 0; k < K; ++k) {
+        const SelJob& s = sel[(size_t)b * K + k];
+        if (s.kind != 0) continue;
+        SubJob jb;
+        jb.sub_off = s.sub_off;
+        jb.S = s.S;
+        jb.score_off = s.score_off + (long long)tile * Wt;
+        jb.spec_base = spec_base;
+        jb.blk_lo = (int)blk_lo;
+        jb.blk_hi = (int)std::min<long long>(blk_hi, ceil_div64(s.S, L));
+        jb.n_out = Wt;
+        jb.energy_slot = s.energy_slot + tile;
+        jobs.push_back(jb);
+      }
+    }
+  }
+  B2_TRY(flush());
+
+  MetaArena a;
+  B2_TRY(b2i_meta_begin(h, &a, J * sizeof(SelJob) + 256));
+  const SelJob* d_sel = (const SelJob*)b2i_meta_put(&a, sel.data(), J * sizeof(SelJob));
+  B2_TRY(b2i_meta_commit(&a));
+  select_candidates_kernel<<<(unsigned)J, 256, 0, h->stream>>>(d_sel, scores, job_energy, cand_off,
+                                                                cand_cnt);
+  B2_CHECK_LAUNCH(h, "select_candidates_kernel");
+  if (J > 65535) B2_FAIL(h, B2_ERR_UNSUPPORTED, "align: B*K > 65535 in one call");
+  rescore_kernel<<<dim3(kCandMax, (unsigned)J), 256, 0, h->stream>>>(d_sel, d_ref, d_sub, cand_off,
+                                                                      cand_cnt, cand_score);
+  B2_CHECK_LAUNCH(h, "rescore_kernel");
+  pick_kernel<<<(unsigned)((J + 127) / 128), 128, 0, h->stream>>>(d_sel, (int)J, cand_off, cand_cnt,
+                                                                   cand_score, d_score, d_offset,
+                                                                   d_status);
+  B2_CHECK_LAUNCH(h, "pick_kernel");
+  return B2_OK;
+}

@@ -1,0 +1,456 @@
+// Device building blocks of the windowed cross-correlation (K3-K5): an in-place, shared-memory
+// resident, mixed-radix (16,16,16,4) complex FFT of M = 2^14 points that carries one real block
+// of P = 2^15 samples (even/odd packing), the real-FFT untangle / retangle performed directly in
+// the digit-reversed ("position") order the decimation-in-frequency passes leave behind, and
+// the decimation-in-time inverse.  The data flow is modelled and checked against np.fft in
+// tests/fft_model.py.
+#pragma once
+#include <cuda_runtime.h>
+#include <math.h>
+#include <stdint.h>
+
+// Everything here is __host__ __device__ so that tests/host_emul/corr_emul.cu can run the exact
+// kernel code thread by thread on the CPU (the build container has no GPU).
+#define CORR_HD __host__ __device__ __forceinline__
+#ifdef __CUDA_ARCH__
+#define CORR_LDG(p) __ldg(p)
+#define CORR_SYNC() __syncthreads()
+#else
+#define CORR_LDG(p) (*(p))
+#define CORR_SYNC() ((void)0)
+#endif
+
+namespace corr {
+
+constexpr int kM = 16384;        // complex points per block transform
+constexpr int kP = 2 * kM;       // real samples per block
+constexpr int kThreads = 512;
+constexpr int kPairs = kM / 2;   // (position, partner) pairs of the packed half spectrum
+
+// Shared-memory layout (dynamic): float2 buf[kM] | float2 tw1024[1024] | float2 fine32[32]
+constexpr size_t kSmemBytes = (size_t)kM * 8 + 1024 * 8 + 32 * 8 + 256;
+
+// XOR swizzle of the complex index: makes every pass (strides 1024, 64, 4, 1) and the
+// untangle's mirrored partner access bank-conflict free for 8-byte accesses.
+CORR_HD int swz(int i) { return i ^ ((i >> 4) & 3) ^ (((i >> 6) & 3) << 2); }
+
+CORR_HD float2 cmul(float2 a, float2 b) {
+  return make_float2(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x);
+}
+CORR_HD float2 cmul_conj_a(float2 a, float2 b) {  // conj(a) * b
+  return make_float2(a.x * b.x + a.y * b.y, a.x * b.y - a.y * b.x);
+}
+CORR_HD float2 cadd(float2 a, float2 b) { return make_float2(a.x + b.x, a.y + b.y); }
+CORR_HD float2 csub(float2 a, float2 b) { return make_float2(a.x - b.x, a.y - b.y); }
+CORR_HD float2 cconj(float2 a) { return make_float2(a.x, -a.y); }
+
+// position <-> frequency of the in-place DIF output, radices (16,16,16,4)
+CORR_HD int freq_of_pos(int p) {
+  return (p >> 10) | (((p >> 6) & 15) << 4) | (((p >> 2) & 15) << 8) | ((p & 3) << 12);
+}
+CORR_HD int pos_of_freq(int f) {
+  return ((f & 15) << 10) | (((f >> 4) & 15) << 6) | (((f >> 8) & 15) << 2) | (f >> 12);
+}
+CORR_HD int partner_pos(int p) {
+  return pos_of_freq((kM - freq_of_pos(p)) & (kM - 1));
+}
+
+struct Tables {
+  const float2* tw1024;  // exp(-2 pi i t / 1024)
+  const float2* fine32;  // exp(-2 pi i t / 32768), t < 32
+};
+
+CORR_HD void init_tables(float2* tw1024, float2* fine32, int tid) {
+  for (int t = tid; t < 1024; t += kThreads) {
+    float s, c;
+    sincospif(-(float)t * (1.0f / 512.0f), &s, &c);
+    tw1024[t] = make_float2(c, s);
+  }
+  if (tid < 32) {
+    float s, c;
+    sincospif(-(float)tid * (1.0f / 16384.0f), &s, &c);
+    fine32[tid] = make_float2(c, s);
+  }
+}
+
+// exp(-2 pi i a / 32768) for a in [0, 32768)
+CORR_HD float2 twiddle15(const Tables& t, int a) {
+  return cmul(t.tw1024[a >> 5], t.fine32[a & 31]);
+}
+
+// 4-point DFT in place: forward uses exp(-i pi/2 q k), inverse the conjugate.
+template <bool INV>
+CORR_HD void r4(float2& a0, float2& a1, float2& a2, float2& a3) {
+  const float2 t0 = cadd(a0, a2), t1 = csub(a0, a2), t2 = cadd(a1, a3), t3 = csub(a1, a3);
+  a0 = cadd(t0, t2);
+  a2 = csub(t0, t2);
+  if (!INV) {
+    a1 = make_float2(t1.x + t3.y, t1.y - t3.x);
+    a3 = make_float2(t1.x - t3.y, t1.y + t3.x);
+  } else {
+    a1 = make_float2(t1.x - t3.y, t1.y + t3.x);
+    a3 = make_float2(t1.x + t3.y, t1.y - t3.x);
+  }
+}
+
+// multiply by exp(-+ 2 pi i n / 16) (forward: -, inverse: +)
+template <bool INV, int N>
+CORR_HD float2 rot16(float2 v) {
+  constexpr float c1 = 0.92387953251128674f, s1 = 0.38268343236508977f, r = 0.70710678118654752f;
+  constexpr int n = N & 15;
+  float cr, ci;
+  if (n == 0) return v;
+  if (n == 1) { cr = c1; ci = -s1; }
+  else if (n == 2) { cr = r; ci = -r; }
+  else if (n == 3) { cr = s1; ci = -c1; }
+  else if (n == 4) { return INV ? make_float2(-v.y, v.x) : make_float2(v.y, -v.x); }
+  else if (n == 6) { cr = -r; ci = -r; }
+  else if (n == 9) { cr = -c1; ci = s1; }
+  else { cr = 1.f; ci = 0.f; }
+  if (INV) ci = -ci;
+  return make_float2(v.x * cr - v.y * ci, v.x * ci + v.y * cr);
+}
+
+// 16-point DIF butterfly with the pass twiddles w^(j k) folded in.
+// In:  v[q]      = x[j + q*sub],           q = q_lo + 4 q_hi
+// Out: v[4a + b] = X[k = a + 4b] * w1^k    (to be stored at j + k*sub)
+// w1 = w_span^j (forward twiddle).  Twiddle powers come from a short product chain (depth <= 4).
+CORR_HD void bfly16_dif(float2 (&v)[16], float2 w1) {
+#pragma unroll
+  for (int q = 0; q < 4; ++q) r4<false>(v[q], v[q + 4], v[q + 8], v[q + 12]);
+  const float2 w2 = cmul(w1, w1);
+  const float2 w3 = cmul(w2, w1);
+  // a = 1 (v[4..7]), a = 2 (v[8..11]), a = 3 (v[12..15]); q_lo = index - 4a
+  v[4] = cmul(v[4], w1);
+  v[5] = rot16<false, 1>(cmul(v[5], w1));
+  v[6] = rot16<false, 2>(cmul(v[6], w1));
+  v[7] = rot16<false, 3>(cmul(v[7], w1));
+  v[8] = cmul(v[8], w2);
+  v[9] = rot16<false, 2>(cmul(v[9], w2));
+  v[10] = rot16<false, 4>(cmul(v[10], w2));
+  v[11] = rot16<false, 6>(cmul(v[11], w2));
+  v[12] = cmul(v[12], w3);
+  v[13] = rot16<false, 3>(cmul(v[13], w3));
+  v[14] = rot16<false, 6>(cmul(v[14], w3));
+  v[15] = rot16<false, 9>(cmul(v[15], w3));
+#pragma unroll
+  for (int a = 0; a < 4; ++a) r4<false>(v[4 * a], v[4 * a + 1], v[4 * a + 2], v[4 * a + 3]);
+  const float2 w4 = cmul(w2, w2);
+  const float2 w8 = cmul(w4, w4);
+  const float2 w12 = cmul(w8, w4);
+#pragma unroll
+  for (int a = 0; a < 4; ++a) {
+    v[4 * a + 1] = cmul(v[4 * a + 1], w4);
+    v[4 * a + 2] = cmul(v[4 * a + 2], w8);
+    v[4 * a + 3] = cmul(v[4 * a + 3], w12);
+  }
+}
+
+// Exact mirror: In v[4a+b] = Y[k = a+4b] (from j + k*sub); Out v[q] = 16-point inverse DFT of
+// Y[k] * conj(w1)^k, to be stored at j + q*sub.  w1c = conj(w_span^j).
+CORR_HD void bfly16_dit(float2 (&v)[16], float2 w1c) {
+  const float2 w2 = cmul(w1c, w1c);
+  const float2 w3 = cmul(w2, w1c);
+  const float2 w4 = cmul(w2, w2);
+  const float2 w8 = cmul(w4, w4);
+  const float2 w12 = cmul(w8, w4);
+#pragma unroll
+  for (int a = 0; a < 4; ++a) {
+    v[4 * a + 1] = cmul(v[4 * a + 1], w4);
+    v[4 * a + 2] = cmul(v[4 * a + 2], w8);
+    v[4 * a + 3] = cmul(v[4 * a + 3], w12);
+  }
+#pragma unroll
+  for (int a = 0; a < 4; ++a) r4<true>(v[4 * a], v[4 * a + 1], v[4 * a + 2], v[4 * a + 3]);
+  v[4] = cmul(v[4], w1c);
+  v[5] = cmul(rot16<true, 1>(v[5]), w1c);
+  v[6] = cmul(rot16<true, 2>(v[6]), w1c);
+  v[7] = cmul(rot16<true, 3>(v[7]), w1c);
+  v[8] = cmul(v[8], w2);
+  v[9] = cmul(rot16<true, 2>(v[9]), w2);
+  v[10] = cmul(rot16<true, 4>(v[10]), w2);
+  v[11] = cmul(rot16<true, 6>(v[11]), w2);
+  v[12] = cmul(v[12], w3);
+  v[13] = cmul(rot16<true, 3>(v[13]), w3);
+  v[14] = cmul(rot16<true, 6>(v[14]), w3);
+  v[15] = cmul(rot16<true, 9>(v[15]), w3);
+#pragma unroll
+  for (int q = 0; q < 4; ++q) r4<true>(v[q], v[q + 4], v[q + 8], v[q + 12]);
+}
+
+// forward twiddle w_span^j for the radix-16 pass whose element stride is 2^SUB_LOG2
+template <int SUB_LOG2>
+CORR_HD float2 pass_twiddle(const Tables& t, int j) {
+  if (SUB_LOG2 == 10) return twiddle15(t, j << 1);  // span 16384
+  if (SUB_LOG2 == 6) return t.tw1024[j];            // span 1024
+  return t.tw1024[j << 4];                          // span 64
+}
+
+// One in-place radix-16 DIF pass over shared memory (spans 1024 and 64).
+template <int SUB_LOG2>
+CORR_HD void dif16_pass_smem(float2* buf, const Tables& t, int tid) {
+#pragma unroll 1
+  for (int rep = 0; rep < 2; ++rep) {
+    const int u = tid + rep * kThreads;
+    const int j = u & ((1 << SUB_LOG2) - 1);
+    const int base = ((u >> SUB_LOG2) << (SUB_LOG2 + 4)) + j;
+    float2 v[16];
+#pragma unroll
+    for (int q = 0; q < 16; ++q) v[q] = buf[swz(base + (q << SUB_LOG2))];
+    bfly16_dif(v, pass_twiddle<SUB_LOG2>(t, j));
+#pragma unroll
+    for (int a = 0; a < 4; ++a)
+#pragma unroll
+      for (int b = 0; b < 4; ++b) buf[swz(base + ((a + 4 * b) << SUB_LOG2))] = v[4 * a + b];
+  }
+}
+
+template <int SUB_LOG2>
+CORR_HD void dit16_pass_smem(float2* buf, const Tables& t, int tid) {
+#pragma unroll 1
+  for (int rep = 0; rep < 2; ++rep) {
+    const int u = tid + rep * kThreads;
+    const int j = u & ((1 << SUB_LOG2) - 1);
+    const int base = ((u >> SUB_LOG2) << (SUB_LOG2 + 4)) + j;
+    float2 v[16];
+#pragma unroll
+    for (int a = 0; a < 4; ++a)
+#pragma unroll
+      for (int b = 0; b < 4; ++b) v[4 * a + b] = buf[swz(base + ((a + 4 * b) << SUB_LOG2))];
+    bfly16_dit(v, cconj(pass_twiddle<SUB_LOG2>(t, j)));
+#pragma unroll
+    for (int q = 0; q < 16; ++q) buf[swz(base + (q << SUB_LOG2))] = v[q];
+  }
+}
+
+// last DIF pass / first DIT pass: radix 4 on 4 contiguous points, no twiddles
+template <bool INV>
+CORR_HD void r4_pass_smem(float2* buf, int tid) {
+#pragma unroll 2
+  for (int rep = 0; rep < kM / 4 / kThreads; ++rep) {
+    const int base = (tid + rep * kThreads) << 2;
+    float2 a0 = buf[swz(base)], a1 = buf[swz(base + 1)], a2 = buf[swz(base + 2)],
+           a3 = buf[swz(base + 3)];
+    r4<INV>(a0, a1, a2, a3);
+    buf[swz(base)] = a0;
+    buf[swz(base + 1)] = a1;
+    buf[swz(base + 2)] = a2;
+    buf[swz(base + 3)] = a3;
+  }
+}
+
+// A real block as the kernels see it: value(t) = 2*src[t]-1 for t in [t_lo, t_hi), else 0.
+struct BlockSource {
+  const float* src;  // may point outside the array; only [t_lo, t_hi) is dereferenced
+  int t_lo, t_hi;
+};
+
+CORR_HD float2 load_pair(const BlockSource& s, int n, bool vec_ok) {
+  const int t = 2 * n;
+  float2 r = make_float2(0.f, 0.f);
+  if (vec_ok && t >= s.t_lo && t + 1 < s.t_hi) {
+    const float2 x = CORR_LDG(reinterpret_cast<const float2*>(s.src + t));
+    r.x = 2.f * x.x - 1.f;
+    r.y = 2.f * x.y - 1.f;
+  } else {
+    if (t >= s.t_lo && t < s.t_hi) r.x = 2.f * CORR_LDG(s.src + t) - 1.f;
+    if (t + 1 >= s.t_lo && t + 1 < s.t_hi) r.y = 2.f * CORR_LDG(s.src + t + 1) - 1.f;
+  }
+  return r;
+}
+
+// First DIF pass (span 16384) reading the block straight from global memory.
+// Returns the thread's partial sum of squares of the (transformed) samples it loaded.
+CORR_HD float dif16_pass1_global(float2* buf, const Tables& t, int tid,
+                                                    const BlockSource& s) {
+  const bool vec_ok = (reinterpret_cast<uintptr_t>(s.src) & 7) == 0;
+  float ss = 0.f;
+#pragma unroll 1
+  for (int rep = 0; rep < 2; ++rep) {
+    const int j = tid + rep * kThreads;
+    float2 v[16];
+#pragma unroll
+    for (int q = 0; q < 16; ++q) v[q] = load_pair(s, j + (q << 10), vec_ok);
+#pragma unroll
+    for (int q = 0; q < 16; ++q) ss += v[q].x * v[q].x + v[q].y * v[q].y;
+    bfly16_dif(v, pass_twiddle<10>(t, j));
+#pragma unroll
+    for (int a = 0; a < 4; ++a)
+#pragma unroll
+      for (int b = 0; b < 4; ++b) buf[swz(j + ((a + 4 * b) << 10))] = v[4 * a + b];
+  }
+  return ss;
+}
+
+// Forward transform of one real block: on return (after the trailing __syncthreads) buf holds
+// DFT_M of z[n] = x[2n] + i x[2n+1] in position order.  The caller must have synchronised all
+// readers of buf before calling.
+CORR_HD float forward_block(float2* buf, const Tables& t, int tid,
+                                               const BlockSource& s) {
+  const float ss = dif16_pass1_global(buf, t, tid, s);
+  CORR_SYNC();
+  dif16_pass_smem<6>(buf, t, tid);
+  CORR_SYNC();
+  dif16_pass_smem<2>(buf, t, tid);
+  CORR_SYNC();
+  r4_pass_smem<false>(buf, tid);
+  CORR_SYNC();
+  return ss;
+}
+
+// Packed half spectrum (x2) of the real block at an even position p and its partner q:
+//   H[p] = E - i T,  H[q] = conj(E) - i conj(T),  E = Z[p] + conj Z[q],  T = w^f (Z[p] - conj Z[q])
+CORR_HD void untangle_pair(const float2* buf, const Tables& t, int p, int q,
+                                              float2& hp, float2& hq) {
+  const float2 zp = buf[swz(p)];
+  const float2 zq = buf[swz(q)];
+  const float2 e = make_float2(zp.x + zq.x, zp.y - zq.y);
+  const float2 d = make_float2(zp.x - zq.x, zp.y + zq.y);
+  const float2 tt = cmul(twiddle15(t, freq_of_pos(p)), d);
+  hp = make_float2(e.x + tt.y, e.y - tt.x);
+  hq = make_float2(e.x - tt.y, -e.y - tt.x);
+}
+
+// Same value for one arbitrary position (used for the four special positions 0..3).
+CORR_HD float2 untangle_one(const float2* buf, const Tables& t, int p) {
+  const int q = partner_pos(p);
+  const float2 zp = buf[swz(p)];
+  const float2 zq = buf[swz(q)];
+  const float2 e = make_float2(zp.x + zq.x, zp.y - zq.y);
+  const float2 d = make_float2(zp.x - zq.x, zp.y + zq.y);
+  const float2 tt = cmul(twiddle15(t, freq_of_pos(p)), d);
+  return make_float2(e.x + tt.y, e.y - tt.x);
+}
+
+// Thread-to-pair map shared by the producer (reference spectra) and the consumer (subtitle
+// blocks): pair r = tid + u*kThreads covers even position p = 2r and its partner (always odd).
+// The four positions whose partner is not of that form are handled by pairs 0 and 1:
+//   pair 0 = (position 0: DC and Nyquist bins packed as (re, im); position 2: f = M/2, its own
+//             partner),  pair 1 = (position 1, position 3), each other's partners.
+CORR_HD void slot_positions(int r, int& p, int& q) {
+  if (r >= 2) {
+    p = 2 * r;
+    q = partner_pos(p);
+  } else if (r == 0) {
+    p = 0;
+    q = 2;
+  } else {
+    p = 1;
+    q = 3;
+  }
+}
+
+CORR_HD void untangle_slot(const float2* buf, const Tables& t, int r, float2& hp, float2& hq) {
+  if (r >= 2) {
+    const int p = 2 * r;
+    untangle_pair(buf, t, p, partner_pos(p), hp, hq);
+  } else if (r == 0) {
+    const float2 z0 = buf[swz(0)];
+    hp = make_float2(2.f * (z0.x + z0.y), 2.f * (z0.x - z0.y));
+    hq = untangle_one(buf, t, 2);
+  } else {
+    untangle_pair(buf, t, 1, 3, hp, hq);
+  }
+}
+
+// Inverse of the packing for the accumulated product spectrum C (position order):
+//   Zc[p] = E' + i T',  Zc[q] = conj(E') + i conj(T'),  E' = C[p] + conj C[q],
+//   T' = conj(w^f) (C[p] - conj C[q])
+CORR_HD void retangle_pair(const Tables& t, int p, float2 cp, float2 cq,
+                                              float2& zp, float2& zq) {
+  const float2 e = make_float2(cp.x + cq.x, cp.y - cq.y);
+  const float2 d = make_float2(cp.x - cq.x, cp.y + cq.y);
+  const float2 tt = cmul(cconj(twiddle15(t, freq_of_pos(p))), d);
+  zp = make_float2(e.x - tt.y, e.y + tt.x);
+  zq = make_float2(e.x + tt.y, -e.y + tt.x);
+}
+
+// ---- per-thread phases of the two kernels (also driven by tests/host_emul/corr_emul.cu) ------
+
+struct SubState {
+  float2 cp[16];  // accumulated conj(A) * B at the even position of each of the thread's 16 pairs
+  float2 cq[16];  // ... and at its partner
+  float ss;       // sum of squares of the subtitle samples this thread loaded
+};
+
+CORR_HD void sub_state_clear(SubState& st) {
+#pragma unroll
+  for (int u = 0; u < 16; ++u) {
+    st.cp[u] = make_float2(0.f, 0.f);
+    st.cq[u] = make_float2(0.f, 0.f);
+  }
+  st.ss = 0.f;
+}
+
+// Producer: packed half spectrum (x2) of the reference block in buf -> spec[kPairs] float4.
+CORR_HD void spec_store(const float2* buf, const Tables& t, int tid, float4* spec) {
+#pragma unroll 4
+  for (int u = 0; u < 16; ++u) {
+    const int r = tid + u * kThreads;
+    float2 hp, hq;
+    untangle_slot(buf, t, r, hp, hq);
+    spec[r] = make_float4(hp.x, hp.y, hq.x, hq.y);
+  }
+}
+
+// Consumer: acc += conj(A) * B for the subtitle block spectrum in buf and the stored B.
+CORR_HD void sub_accumulate(SubState& st, const float2* buf, const Tables& t, int tid,
+                            const float4* spec) {
+#pragma unroll
+  for (int u = 0; u < 16; ++u) {
+    const int r = tid + u * kThreads;
+    float2 hp, hq;
+    untangle_slot(buf, t, r, hp, hq);
+    const float4 b = CORR_LDG(spec + r);
+    float2 dp;
+    if (u == 0 && tid == 0) {
+      dp = make_float2(hp.x * b.x, hp.y * b.y);  // two real bins: DC and Nyquist
+    } else {
+      dp = cmul_conj_a(hp, make_float2(b.x, b.y));
+    }
+    const float2 dq = cmul_conj_a(hq, make_float2(b.z, b.w));
+    st.cp[u] = cadd(st.cp[u], dp);
+    st.cq[u] = cadd(st.cq[u], dq);
+  }
+}
+
+// Consumer, after the last block: accumulated spectrum -> position-order input of the inverse
+// transform, written into buf (every position is written exactly once).
+CORR_HD void sub_retangle_store(const SubState& st, float2* buf, const Tables& t, int tid) {
+#pragma unroll
+  for (int u = 0; u < 16; ++u) {
+    const int r = tid + u * kThreads;
+    float2 zp, zq;
+    if (u == 0 && tid == 0) {
+      const float c0 = st.cp[0].x, cm = st.cp[0].y;
+      zp = make_float2(c0 + cm, c0 - cm);
+      float2 unused;
+      retangle_pair(t, 2, st.cq[0], st.cq[0], zq, unused);
+      buf[swz(0)] = zp;
+      buf[swz(2)] = zq;
+    } else {
+      int p, q;
+      slot_positions(r, p, q);
+      retangle_pair(t, p, st.cp[u], st.cq[u], zp, zq);
+      buf[swz(p)] = zp;
+      buf[swz(q)] = zq;
+    }
+  }
+}
+
+// Inverse transform of buf (position order in, natural order out).  Needs a barrier before
+// (all retangle stores visible) and leaves one after.
+CORR_HD void inverse_passes_1(float2* buf, int tid) { r4_pass_smem<true>(buf, tid); }
+CORR_HD void inverse_passes_2(float2* buf, const Tables& t, int tid) { dit16_pass_smem<2>(buf, t, tid); }
+CORR_HD void inverse_passes_3(float2* buf, const Tables& t, int tid) { dit16_pass_smem<6>(buf, t, tid); }
+CORR_HD void inverse_passes_4(float2* buf, const Tables& t, int tid) { dit16_pass_smem<10>(buf, t, tid); }
+
+// c[m] for the window: real/imag parts of the natural-order inverse output interleave.
+// The transforms are unnormalised and the spectra carry factors 2 (A), 2 (B), 2 (retangle).
+constexpr float kOutScale = 1.0f / (8.0f * (float)kM);
+CORR_HD float window_value(const float2* buf, int m) {
+  const float2 z = buf[swz(m >> 1)];
+  return ((m & 1) ? z.y : z.x) * kOutScale;
+}
+
+}  // namespace corr

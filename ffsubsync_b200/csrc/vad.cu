@@ -1,0 +1,317 @@
+// K1: fused frame-energy / zero-crossing VAD over 10 ms windows of s16le PCM, and the
+// counter-hash PCM synthesiser used by tests and bench.
+//
+// Replaces the per-window detector loop of the reference
+// (ffsubsync/speech_transformers.py:155-183 called from :710-753): for every window of
+// fpw = int(frame_rate/sample_rate + 0.5) samples emit 1.0 (speech) or non_speech_label.
+// Rule (oracle/vad_oracle.py): E = sum x^2 (int64), Z = sign changes inside the
+// window; speech <=> E >= fpw*energy_threshold and z_lo <= Z <= z_hi; a trailing partial
+// window is non-speech.
+//
+// Roofline: pure HBM stream, 2*fpw bytes in -> 4 bytes out per window (320 B -> 4 B at 16 kHz).
+// Persistent CTAs; each tile of TW windows is moved HBM -> shared memory by one 1-D TMA bulk
+// copy (cp.async.bulk + mbarrier complete_tx, SASS UBLKCP) into a STAGES-deep ring so that
+// >= 60 KB per SM is in flight; consumers read the staged windows with conflict-free LDS.128.
+#include "common.cuh"
+
+namespace {
+
+constexpr int kThreads = 256;
+constexpr int kStages = 4;
+
+struct TileDesc {
+  long long out_base;   // index into out[] of the tile's first window
+  long long n_left;     // samples of the signal from the tile's first sample to the signal end
+  int n_windows;        // windows in this tile (0 = no more tiles for this CTA)
+  int head_bytes;       // offset of the first sample inside the 16 B-aligned staged span
+  int tail_src_off;     // >=0: bytes [tail_src_off, tail_end) of the span must be copied by hand
+  int tail_end;
+  long long span_gbyte; // global byte address offset of the staged span start
+};
+
+struct VadParams {
+  const unsigned char* pcm_bytes;
+  float* out;
+  const long long* pcm_off;   // [B+1] samples
+  const long long* out_off;   // [B+1] windows
+  const long long* tile_off;  // [B+1] tiles
+  long long total_tiles;
+  long long pcm_total_bytes;
+  long long e_min;            // fpw * energy_threshold
+  int B, fpw, G, tw, z_lo, z_hi, fast, stage_bytes;
+  float label;
+};
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) {
+  return (uint32_t)__cvta_generic_to_shared(p);
+}
+__device__ __forceinline__ void mbar_init(uint64_t* bar, int count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)),
+               "r"(bytes)
+               : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "WAIT_%=:\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+      "@p bra DONE_%=;\n\t"
+      "bra WAIT_%=;\n\t"
+      "DONE_%=:\n\t"
+      "}" ::"r"(smem_u32(bar)),
+      "r"(parity)
+      : "memory");
+}
+// 1-D TMA bulk copy global -> shared, completion signalled on an mbarrier.
+__device__ __forceinline__ void tma_bulk_g2s(void* dst, const void* src, uint32_t bytes,
+                                             uint64_t* bar) {
+  asm volatile(
+      "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::
+          "r"(smem_u32(dst)),
+      "l"(src), "r"(bytes), "r"(smem_u32(bar))
+      : "memory");
+}
+
+__device__ __forceinline__ void accum_word(uint32_t w, uint32_t prev, long long& e, int& z) {
+  int lo = (int)(short)(w & 0xffffu);
+  int hi = ((int)w) >> 16;
+  e += (long long)lo * lo;
+  e += (long long)hi * hi;
+  // f = [x_2k : x_2k-1]; (w ^ f) has the 2k-1 -> 2k sign change in bit 15, 2k -> 2k+1 in bit 31
+  uint32_t f = __funnelshift_l(prev, w, 16);
+  z += __popc((w ^ f) & 0x80008000u);
+}
+
+__global__ void __launch_bounds__(kThreads) vad_energy_zcr_kernel(VadParams p) {
+  extern __shared__ __align__(128) unsigned char smem[];
+  unsigned char* data = smem;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + (size_t)kStages * p.stage_bytes);
+  TileDesc* descs = reinterpret_cast<TileDesc*>(bars + kStages);
+
+  const int tid = threadIdx.x;
+  if (tid == 0) {
+    for (int s = 0; s < kStages; ++s) mbar_init(&bars[s], 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+
+  // ---- producer state (thread 0 only) ----
+  int cur_b = 0;
+  auto issue = [&](long long t, int stage) {
+    TileDesc d;
+    if (t >= p.total_tiles) {
+      d.n_windows = 0;
+      d.out_base = d.n_left = d.span_gbyte = 0;
+      d.head_bytes = 0;
+      d.tail_src_off = -1;
+      d.tail_end = 0;
+      descs[stage] = d;
+      mbar_arrive(&bars[stage]);
+      return;
+    }
+    while (t >= p.tile_off[cur_b + 1]) ++cur_b;
+    const long long w0 = (t - p.tile_off[cur_b]) * p.tw;
+    const long long sig0 = p.pcm_off[cur_b], sig1 = p.pcm_off[cur_b + 1];
+    const long long n = sig1 - sig0;
+    const long long nwin = (n + p.fpw - 1) / p.fpw;
+    const int nw = (int)min((long long)p.tw, nwin - w0);
+    const long long s0 = sig0 + w0 * p.fpw;
+    const long long s1 = min(s0 + (long long)nw * p.fpw, sig1);
+    const long long b0 = 2 * s0, b1 = 2 * s1;
+    const long long a0 = b0 & ~15LL;
+    const long long a1 = (b1 + 15) & ~15LL;
+    const long long limit = p.pcm_total_bytes & ~15LL;  // bulk copies stay inside the buffer
+    const long long bulk_end = min(a1, limit);
+    const uint32_t bulk = bulk_end > a0 ? (uint32_t)(bulk_end - a0) : 0u;
+    d.n_windows = nw;
+    d.out_base = p.out_off[cur_b] + w0;
+    d.n_left = sig1 - s0;
+    d.head_bytes = (int)(b0 - a0);
+    d.span_gbyte = a0;
+    if (bulk_end < b1) {  // ragged end of the whole buffer: < 16 bytes copied by hand
+      d.tail_src_off = (int)(max(bulk_end, a0) - a0);
+      d.tail_end = (int)(b1 - a0);
+    } else {
+      d.tail_src_off = -1;
+      d.tail_end = 0;
+    }
+    descs[stage] = d;
+    if (bulk) {
+      mbar_arrive_expect_tx(&bars[stage], bulk);
+      tma_bulk_g2s(data + (size_t)stage * p.stage_bytes, p.pcm_bytes + a0, bulk, &bars[stage]);
+    } else {
+      mbar_arrive(&bars[stage]);
+    }
+  };
+
+  const long long first = blockIdx.x, stride = gridDim.x;
+  if (tid == 0) {
+    for (int s = 0; s < kStages - 1; ++s) issue(first + (long long)s * stride, s);
+  }
+
+  const int G = p.G;
+  const int g = tid % G;
+  const int wl = tid / G;
+  const int fpw = p.fpw;
+
+  for (long long it = 0;; ++it) {
+    const int stage = (int)(it % kStages);
+    const uint32_t parity = (uint32_t)((it / kStages) & 1);
+    if (tid == 0) issue(first + (it + kStages - 1) * stride, (int)((it + kStages - 1) % kStages));
+    mbar_wait(&bars[stage], parity);
+    const TileDesc d = descs[stage];
+    if (d.n_windows == 0) break;  // uniform: tiles are handed out in increasing order
+    unsigned char* span = data + (size_t)stage * p.stage_bytes;
+    if (d.tail_src_off >= 0) {  // rare: last < 16 bytes of the whole PCM buffer
+      const int nb = d.tail_end - d.tail_src_off;
+      if (tid < nb) span[d.tail_src_off + tid] = p.pcm_bytes[d.span_gbyte + d.tail_src_off + tid];
+      __syncthreads();
+    }
+    long long e = 0;
+    int z = 0;
+    const bool active = wl < d.n_windows;
+    const long long left = d.n_left - (long long)wl * fpw;  // samples from window start to signal end
+    const bool full = active && left >= fpw;
+    const unsigned char* wbase = span + d.head_bytes + (size_t)wl * fpw * 2;
+    if (full) {
+      if (p.fast && d.head_bytes == 0) {
+        const int C = fpw >> 3;  // 16-byte chunks per window
+        for (int c = g; c < C; c += G) {
+          const uint4 v = *reinterpret_cast<const uint4*>(wbase + 16 * c);
+          const uint32_t pw =
+              c > 0 ? *reinterpret_cast<const uint32_t*>(wbase + 16 * c - 4) : (v.x << 16);
+          accum_word(v.x, pw, e, z);
+          accum_word(v.y, v.x, e, z);
+          accum_word(v.z, v.y, e, z);
+          accum_word(v.w, v.z, e, z);
+        }
+      } else {
+        const short* xs = reinterpret_cast<const short*>(wbase);
+        for (int i = g; i < fpw; i += G) {
+          const int x = xs[i];
+          const int px = i > 0 ? (int)xs[i - 1] : x;
+          e += (long long)x * x;
+          z += ((x < 0) != (px < 0));
+        }
+      }
+    }
+    for (int off = G >> 1; off > 0; off >>= 1) {
+      e += __shfl_xor_sync(0xffffffffu, e, off);
+      z += __shfl_xor_sync(0xffffffffu, z, off);
+    }
+    if (active && g == 0) {
+      const bool speech = full && e >= p.e_min && z >= p.z_lo && z <= p.z_hi;
+      p.out[d.out_base + wl] = speech ? 1.0f : p.label;
+    }
+    __syncthreads();  // stage fully consumed -> may be refilled by the next issue
+  }
+}
+
+// ------------------------------------------------------------------------------ synthesiser
+__device__ __forceinline__ uint32_t lowbias32(uint32_t x) {
+  x ^= x >> 16;
+  x *= 0x7feb352du;
+  x ^= x >> 15;
+  x *= 0x846ca68bu;
+  x ^= x >> 16;
+  return x;
+}
+
+__global__ void __launch_bounds__(256) synth_pcm_kernel(const uint8_t* __restrict__ cls,
+                                                         long long n_windows, int fpw,
+                                                         uint32_t seed, short* __restrict__ out) {
+  const long long n = n_windows * (long long)fpw;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n;
+       i += (long long)gridDim.x * blockDim.x) {
+    const long long w = i / fpw;
+    const int pos = (int)(i - w * fpw);
+    const uint32_t hsh = lowbias32(((uint32_t)i) ^ seed);
+    const int c = cls[w];
+    int v;
+    if (c == 0)
+      v = (int)((hsh >> 26) & 0x3fu) - 32;
+    else if (c == 1)
+      v = ((((pos / 40) & 1) == 0) ? 6000 : -6000) + (int)((hsh >> 14) & 0xfffu) - 2048;
+    else
+      v = (int)(hsh & 0x3fffu) - 8192;
+    out[i] = (short)v;
+  }
+}
+
+}  // namespace
+
+int b2i_synth_launch(b2_ctx* h, const uint8_t* d_cls, int64_t n_windows, int fpw, uint32_t seed,
+                     int16_t* d_out) {
+  long long n = n_windows * (long long)fpw;
+  int blocks = (int)std::min<long long>((n + 255) / 256, (long long)h->sm_count * 16);
+  synth_pcm_kernel<<<blocks, 256, 0, h->stream>>>(d_cls, n_windows, fpw, seed, (short*)d_out);
+  B2_CHECK_LAUNCH(h, "synth_pcm_kernel");
+  return B2_OK;
+}
+
+int b2i_vad_launch(b2_ctx* h, const int16_t* d_pcm, const int64_t* pcm_off, int B, int fpw,
+                   float non_speech_label, int64_t energy_threshold, int z_lo, int z_hi,
+                   float* d_out, const int64_t* out_off) {
+  if (((uintptr_t)d_pcm & 15) != 0)
+    B2_FAIL(h, B2_ERR_BAD_ARG, "vad: device PCM pointer must be 16-byte aligned");
+  VadParams p;
+  // lanes per window: keep >= 2 16-byte chunks per lane when possible
+  const int C = fpw / 8;
+  int G = 4;
+  if (C > 32) G = 8;
+  if (C > 64) G = 16;
+  if (C > 128) G = 32;
+  p.G = G;
+  p.tw = kThreads / G;
+  p.fpw = fpw;
+  p.fast = (fpw % 8 == 0) ? 1 : 0;
+  p.stage_bytes = ((p.tw * fpw * 2 + 32) + 127) & ~127;
+  size_t smem = (size_t)kStages * p.stage_bytes + kStages * sizeof(uint64_t) +
+                kStages * sizeof(TileDesc) + 64;
+  if (smem > 227 * 1024) B2_FAIL(h, B2_ERR_UNSUPPORTED, "vad: window of %d samples too large", fpw);
+
+  std::vector<long long> tile_off(B + 1);
+  tile_off[0] = 0;
+  bool aligned = true;
+  for (int b = 0; b < B; ++b) {
+    long long n = pcm_off[b + 1] - pcm_off[b];
+    long long nwin = (n + fpw - 1) / fpw;
+    tile_off[b + 1] = tile_off[b] + (nwin + p.tw - 1) / p.tw;
+    if (pcm_off[b] % 8 != 0) aligned = false;
+  }
+  if (!aligned) p.fast = 0;  // window starts are not 16-byte aligned in the staged span
+  p.total_tiles = tile_off[B];
+  if (p.total_tiles == 0) return B2_OK;
+
+  MetaArena a;
+  size_t tbl = (size_t)(B + 1) * 8;
+  B2_TRY(b2i_meta_begin(h, &a, 3 * tbl + 256));
+  p.pcm_off = (const long long*)b2i_meta_put(&a, pcm_off, tbl);
+  p.out_off = (const long long*)b2i_meta_put(&a, out_off, tbl);
+  p.tile_off = (const long long*)b2i_meta_put(&a, tile_off.data(), tbl);
+  B2_TRY(b2i_meta_commit(&a));
+
+  p.pcm_bytes = (const unsigned char*)d_pcm;
+  p.out = d_out;
+  p.B = B;
+  p.pcm_total_bytes = 2 * (long long)pcm_off[B];
+  p.e_min = (long long)fpw * (long long)energy_threshold;
+  p.z_lo = z_lo;
+  p.z_hi = z_hi;
+  p.label = non_speech_label;
+
+  B2_CUDA(h, cudaFuncSetAttribute(vad_energy_zcr_kernel,
+                                  cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  int per_sm = (int)std::max<size_t>(1, std::min<size_t>(4, (220 * 1024) / smem));
+  long long grid = std::min<long long>(p.total_tiles, (long long)h->sm_count * per_sm);
+  vad_energy_zcr_kernel<<<(unsigned)grid, kThreads, smem, h->stream>>>(p);
+  B2_CHECK_LAUNCH(h, "vad_energy_zcr_kernel");
+  return B2_OK;
+}

@@ -1,0 +1,340 @@
+"""Signal producers of the hot path with the reference's API (ffsubsync/speech_transformers.py):
+
+  * ``_make_energy_zcr_detector``  - detector factory with the reference's factory signature
+    (:101-103, :155-157); the per-window work runs in the CUDA VAD kernel.
+  * ``VideoSpeechTransformer``      - chunk loop / progress protocol of :609-757 around a detector.
+  * ``SubtitleSpeechTransformer``   - cue rasterisation of :946-984 on the GPU rasteriser.
+  * ``ComputeSpeechFrameBoundariesMixin`` (:299-317), ``DeserializeSpeechTransformer`` (:987-1009),
+    ``make_subtitle_speech_pipeline`` (:56-98), ``_is_metadata`` (:928-943).
+
+Out of scope here: ffprobe/embedded-subtitle extraction, silero/webrtc/
+auditok detectors (third-party wheels), multi-segment sampling.  Other detectors can be plugged
+in through ``DETECTOR_FACTORIES`` with the reference's factory signature.
+"""
+import io
+import logging
+import os
+import re
+import shutil
+import subprocess
+from datetime import timedelta
+from typing import Callable, Dict, List, NamedTuple, Optional, Union
+
+import numpy as np
+
+from . import _native
+from .constants import (
+    DEFAULT_ENERGY_THRESHOLD,
+    DEFAULT_SCALE_FACTOR,
+    DEFAULT_START_SECONDS,
+    SAMPLE_RATE,
+)
+from .sklearn_shim import Pipeline, TransformerMixin
+from .subtitle_transformers import SubtitleScaler
+
+logger: logging.Logger = logging.getLogger(__name__)
+
+
+class ProgressInfo(NamedTuple):
+    """Progress emitted to a ``progress_handler`` during speech extraction
+    (same fields as the reference's, speech_transformers.py:38-53)."""
+
+    processed_seconds: float
+    total_seconds: Optional[float]
+
+    @property
+    def fraction(self) -> Optional[float]:
+        if not self.total_seconds:
+            return None
+        return min(1.0, self.processed_seconds / self.total_seconds)
+
+
+# ------------------------------------------------------------------------------------ detectors
+
+def _make_energy_zcr_detector(
+    sample_rate: int,
+    frame_rate: int,
+    non_speech_label: float,
+    energy_threshold: int = DEFAULT_ENERGY_THRESHOLD,
+    z_lo: Optional[int] = None,
+    z_hi: Optional[int] = None,
+) -> Callable[[Union[bytes, np.ndarray]], np.ndarray]:
+    """Frame-energy / zero-crossing VAD (this package's detector).
+
+    Same contract as the reference's detector factories: the returned callable takes the raw
+    s16le bytes (or a uint8 view) of one chunk and returns one float per 10 ms window
+    (1.0 = speech, ``non_speech_label`` otherwise); a trailing partial window is non-speech."""
+    handle = _native.get_handle()
+    fpw = handle.frames_per_window(frame_rate, sample_rate)
+    if fpw <= 0:
+        raise ValueError("bad frame_rate=%r / sample_rate=%r" % (frame_rate, sample_rate))
+
+    def _detect(asegment) -> np.ndarray:
+        if isinstance(asegment, np.ndarray) and asegment.dtype == np.int16:
+            pcm = np.ascontiguousarray(asegment)
+        else:
+            raw = np.frombuffer(asegment, dtype=np.uint8) if not isinstance(asegment, np.ndarray) \
+                else np.ascontiguousarray(asegment).view(np.uint8)
+            pcm = raw[: (len(raw) // 2) * 2].view("<i2")
+        out, _ = _native.get_handle().vad_energy_zcr(
+            pcm, [0, len(pcm)], frame_rate, sample_rate, non_speech_label, energy_threshold,
+            -1 if z_lo is None else z_lo, -1 if z_hi is None else z_hi)
+        return out.astype(np.float64)
+
+    return _detect
+
+
+#: name fragment looked up in ``VideoSpeechTransformer.vad`` -> factory(sample_rate, frame_rate, label)
+DETECTOR_FACTORIES: Dict[str, Callable[[int, int, float], Callable]] = {
+    "energy": _make_energy_zcr_detector,
+}
+
+
+# ---------------------------------------------------------------------------------- boundaries
+
+class ComputeSpeechFrameBoundariesMixin:
+    def __init__(self) -> None:
+        self.start_frame_: Optional[int] = None
+        self.end_frame_: Optional[int] = None
+
+    @property
+    def num_frames(self) -> Optional[int]:
+        if self.start_frame_ is None or self.end_frame_ is None:
+            return None
+        return self.end_frame_ - self.start_frame_
+
+    def fit_boundaries(self, speech_frames: np.ndarray) -> "ComputeSpeechFrameBoundariesMixin":
+        x = np.asarray(speech_frames, dtype=np.float32)
+        if len(x):
+            first, last = _native.get_handle().first_last_nonzero(x, [0, len(x)])
+            if last[0] >= 0:
+                self.start_frame_ = int(first[0])
+                self.end_frame_ = int(last[0])
+        return self
+
+
+# ----------------------------------------------------------------------------- video / PCM side
+
+_PCM_SUFFIXES = (".pcm", ".raw", ".s16le")
+
+
+class VideoSpeechTransformer(TransformerMixin):
+    """PCM -> 100 Hz speech signal.  ``fit`` accepts what the reference accepts (a media path,
+    decoded through an ffmpeg subprocess when the binary is available) and, because this layer
+    starts at decoded audio, also raw s16le mono PCM directly: bytes / bytearray / int16 or uint8
+    arrays, a binary file object, or a ``.pcm`` / ``.raw`` / ``.s16le`` file."""
+
+    def __init__(
+        self,
+        vad: str,
+        sample_rate: int,
+        frame_rate: int,
+        non_speech_label: float,
+        start_seconds: int = 0,
+        ffmpeg_path: Optional[str] = None,
+        ref_stream: Optional[str] = None,
+        vlc_mode: bool = False,
+        gui_mode: bool = False,
+        max_duration_seconds: Optional[float] = None,
+        extract_audio_first: bool = False,
+        progress_handler: Optional[Callable[["ProgressInfo"], None]] = None,
+    ) -> None:
+        self.vad: str = vad
+        self.sample_rate: int = sample_rate
+        self.frame_rate: int = frame_rate
+        self._non_speech_label: float = non_speech_label
+        self.start_seconds: int = start_seconds
+        self.ffmpeg_path: Optional[str] = ffmpeg_path
+        self.ref_stream: Optional[str] = ref_stream
+        self.vlc_mode: bool = vlc_mode
+        self.gui_mode: bool = gui_mode
+        self.max_duration_seconds: Optional[float] = max_duration_seconds
+        self.extract_audio_first: bool = extract_audio_first
+        self.progress_handler = progress_handler
+        self.video_speech_results_: Optional[np.ndarray] = None
+
+    # -- detector dispatch (speech_transformers.py:655-679) -----------------------------------
+    def _make_detector(self):
+        for key, factory in DETECTOR_FACTORIES.items():
+            if key in self.vad:
+                return factory(self.sample_rate, self.frame_rate, self._non_speech_label)
+        raise ValueError("unknown vad: %s" % self.vad)
+
+    # -- PCM sources -----------------------------------------------------------------------------
+    def _build_ffmpeg_args(self, fname: str) -> List[str]:
+        exe = "ffmpeg"
+        if self.ffmpeg_path:
+            exe = os.path.join(self.ffmpeg_path, "ffmpeg")
+        args = [exe]
+        if self.start_seconds > 0:
+            args += ["-ss", str(timedelta(seconds=self.start_seconds))]
+        if self.max_duration_seconds is not None:
+            args += ["-t", str(timedelta(seconds=self.max_duration_seconds))]
+        args += ["-loglevel", "fatal", "-nostdin", "-i", fname]
+        if self.ref_stream is not None and self.ref_stream.startswith("0:a:"):
+            args += ["-map", self.ref_stream]
+        args += ["-f", "s16le", "-ac", "1", "-acodec", "pcm_s16le", "-af", "aresample=async=1",
+                 "-ar", str(self.frame_rate), "-"]
+        return args
+
+    def _open_source(self, src):
+        """-> (readable with .read(n), total_duration_seconds or None, closer)"""
+        bytes_per_second = 2.0 * self.frame_rate
+        if isinstance(src, np.ndarray):
+            src = np.ascontiguousarray(src).view(np.uint8).tobytes() if src.dtype != np.uint8 else src.tobytes()
+        if isinstance(src, (bytes, bytearray, memoryview)):
+            return io.BytesIO(bytes(src)), len(src) / bytes_per_second, None
+        if hasattr(src, "read"):
+            return src, None, None
+        if isinstance(src, str) and src.lower().endswith(_PCM_SUFFIXES):
+            fh = open(src, "rb")
+            return fh, os.path.getsize(src) / bytes_per_second, fh.close
+        args = self._build_ffmpeg_args(src)
+        if shutil.which(args[0]) is None:
+            raise ValueError(
+                "cannot decode %r: no ffmpeg binary found; pass decoded s16le mono PCM "
+                "(bytes / array / .pcm file) instead" % (src,))
+        proc = subprocess.Popen(args, stdout=subprocess.PIPE, stderr=subprocess.DEVNULL)
+        return proc.stdout, None, proc.wait
+
+    def fit(self, fname, *_) -> "VideoSpeechTransformer":
+        detector = self._make_detector()
+        stream, total_duration, closer = self._open_source(fname)
+        if self.max_duration_seconds is not None and total_duration is not None:
+            total_duration = min(total_duration, self.max_duration_seconds)
+        media_bstring: List[np.ndarray] = []
+        bytes_per_frame = 2
+        bytes_per_window = bytes_per_frame * self.frame_rate // self.sample_rate
+        windows_per_buffer = 10000
+        simple_progress = 0.0
+        try:
+            while True:
+                in_bytes = stream.read(bytes_per_window * windows_per_buffer)
+                if not in_bytes:
+                    break
+                newstuff = len(in_bytes) / float(bytes_per_frame) / self.frame_rate
+                if total_duration is not None and simple_progress + newstuff > total_duration:
+                    newstuff = total_duration - simple_progress
+                simple_progress += newstuff
+                if self.progress_handler is not None:
+                    try:
+                        self.progress_handler(ProgressInfo(processed_seconds=simple_progress,
+                                                           total_seconds=total_duration))
+                    except Exception as e:  # a host-supplied callback must never break syncing
+                        logger.warning("progress_handler raised: %s", e)
+                if self.vlc_mode and total_duration is not None:
+                    print("%d" % int(simple_progress * 100.0 / total_duration), flush=True)
+                media_bstring.append(detector(np.frombuffer(in_bytes, np.uint8)))
+        finally:
+            if closer is not None:
+                closer()
+        if len(media_bstring) == 0:
+            raise ValueError(
+                "Unable to detect speech. "
+                "Perhaps try specifying a different stream / track, or a different vad.")
+        self.video_speech_results_ = np.concatenate(media_bstring)
+        logger.info("total of speech segments: %s", np.sum(self.video_speech_results_))
+        return self
+
+    def transform(self, *_) -> np.ndarray:
+        return self.video_speech_results_
+
+
+# ------------------------------------------------------------------------------- subtitle side
+
+_PAIRED_NESTER = {"(": ")", "{": "}", "[": "]", "（": "）", "【": "】", "「": "」"}
+_MARKUP_TAG = re.compile(r"<[^>]+>")
+_NON_DIALOGUE_SYMBOLS = frozenset("♪♫♬♩\U0001F3B5\U0001F3B6")
+
+
+def _is_metadata(content: str, is_beginning_or_end: bool) -> bool:
+    """Cue text that carries no speech: empty, fully bracketed, music symbols only, or (first /
+    last cue) credits-like lines.  Markup tags are ignored."""
+    text = _MARKUP_TAG.sub("", content).strip()
+    if not text:
+        return True
+    if _PAIRED_NESTER.get(text[0]) == text[-1]:
+        return True
+    if all(ch.isspace() or ch in _NON_DIALOGUE_SYMBOLS for ch in text):
+        return True
+    if is_beginning_or_end:
+        return "english" in text.lower() or " - " in text
+    return False
+
+
+class SubtitleSpeechTransformer(TransformerMixin, ComputeSpeechFrameBoundariesMixin):
+    def __init__(self, sample_rate: int, start_seconds: int = 0, framerate_ratio: float = 1.0) -> None:
+        ComputeSpeechFrameBoundariesMixin.__init__(self)
+        self.sample_rate: int = sample_rate
+        self.start_seconds: int = start_seconds
+        self.framerate_ratio: float = framerate_ratio
+        self.subtitle_speech_results_: Optional[np.ndarray] = None
+        self.max_time_: Optional[float] = None
+
+    def fit(self, subs, *_) -> "SubtitleSpeechTransformer":
+        subs = list(subs)
+        n = len(subs)
+        starts = np.array([s.start.total_seconds() for s in subs], dtype=np.float64)
+        ends = np.array([s.end.total_seconds() for s in subs], dtype=np.float64)
+        keep = np.array([not _is_metadata(s.content, i == 0 or i + 1 == n) for i, s in enumerate(subs)],
+                        dtype=np.uint8)
+        max_time = max([0] + list(ends))
+        self.max_time_ = max_time - self.start_seconds
+        level = min(1.0 / self.framerate_ratio, 1.0)
+        # the cues arrive already scaled (SubtitleScaler ran before us): ratio 1.0 for the times,
+        # explicit level for the value (speech_transformers.py:977)
+        out, _ = _native.get_handle().rasterize(
+            starts, ends, keep, [0, n], [1.0], 1, False, self.sample_rate, float(self.start_seconds),
+            levels=[level])
+        self.subtitle_speech_results_ = out.astype(np.float64)
+        if level != np.float32(level):  # keep the float64 level the reference writes
+            self.subtitle_speech_results_[out != 0] = level
+        self.fit_boundaries(self.subtitle_speech_results_)
+        return self
+
+    def transform(self, *_) -> np.ndarray:
+        assert self.subtitle_speech_results_ is not None
+        return self.subtitle_speech_results_
+
+
+class DeserializeSpeechTransformer(TransformerMixin):
+    def __init__(self, non_speech_label: float) -> None:
+        self._non_speech_label: float = non_speech_label
+        self.deserialized_speech_results_: Optional[np.ndarray] = None
+
+    def fit(self, fname, *_) -> "DeserializeSpeechTransformer":
+        speech = np.load(fname)
+        if hasattr(speech, "files"):
+            if "speech" not in speech.files:
+                raise ValueError('could not find "speech" array in serialized file; only contains: %s'
+                                 % speech.files)
+            speech = speech["speech"]
+        speech[speech < 1.0] = self._non_speech_label
+        self.deserialized_speech_results_ = speech
+        return self
+
+    def transform(self, *_) -> np.ndarray:
+        assert self.deserialized_speech_results_ is not None
+        return self.deserialized_speech_results_
+
+
+def make_subtitle_speech_pipeline(
+    parser,
+    start_seconds: int = DEFAULT_START_SECONDS,
+    scale_factor: Optional[float] = DEFAULT_SCALE_FACTOR,
+    **_ignored,
+) -> Union[Pipeline, Callable[[float], Pipeline]]:
+    """parse -> scale -> speech_extract, or (scale_factor=None) a maker ``ratio -> Pipeline`` for
+    the golden-section search.  Subtitle *parsing* is outside the hot path, so ``parser`` (any
+    transformer whose ``transform`` yields cues) must be supplied by the caller; the reference
+    builds one from a file format (speech_transformers.py:56-98)."""
+
+    def subpipe_maker(framerate_ratio):
+        return Pipeline([
+            ("parse", parser),
+            ("scale", SubtitleScaler(framerate_ratio)),
+            ("speech_extract", SubtitleSpeechTransformer(
+                sample_rate=SAMPLE_RATE, start_seconds=start_seconds, framerate_ratio=framerate_ratio)),
+        ])
+
+    return subpipe_maker if scale_factor is None else subpipe_maker(scale_factor)

@@ -1,0 +1,76 @@
+// CPU emulation of the two correlation kernels of ffsubsync_b200/csrc/corr.cu: the very same
+// __host__ __device__ phase functions (corr.cuh) are run for tid = 0..511 with a loop standing
+// in for each __syncthreads-separated phase.  Test infrastructure (the build container has no
+// GPU); tests/test_corr_emul.py drives it.
+//
+// usage: corr_emul in.bin out.bin
+// in.bin : int32 R, S, o_t, W, L ; float ref[R] ; float sub[S]
+// out.bin: float c[W]  (c[m] ~ sum_j sub'[j] ref'[j + o_t + m]) ; float Es, Er
+#include <stdio.h>
+#include <stdlib.h>
+#include <vector>
+
+#include "../../ffsubsync_b200/csrc/corr.cuh"
+
+using namespace corr;
+
+static void forward_all(float2* buf, const Tables& t, const BlockSource& s, float* ss) {
+  for (int tid = 0; tid < kThreads; ++tid) ss[tid] += dif16_pass1_global(buf, t, tid, s);
+  for (int tid = 0; tid < kThreads; ++tid) dif16_pass_smem<6>(buf, t, tid);
+  for (int tid = 0; tid < kThreads; ++tid) dif16_pass_smem<2>(buf, t, tid);
+  for (int tid = 0; tid < kThreads; ++tid) r4_pass_smem<false>(buf, tid);
+}
+
+int main(int argc, char** argv) {
+  if (argc != 3) return 2;
+  FILE* f = fopen(argv[1], "rb");
+  if (!f) return 3;
+  int hdr[5];
+  if (fread(hdr, 4, 5, f) != 5) return 4;
+  const int R = hdr[0], S = hdr[1], o_t = hdr[2], W = hdr[3], L = hdr[4];
+  std::vector<float> ref(R), sub(S);
+  if (fread(ref.data(), 4, R, f) != (size_t)R) return 4;
+  if (fread(sub.data(), 4, S, f) != (size_t)S) return 4;
+  fclose(f);
+
+  std::vector<float2> buf(kM), tw(1024), fine(32);
+  for (int tid = 0; tid < kThreads; ++tid) init_tables(tw.data(), fine.data(), tid);
+  Tables t{tw.data(), fine.data()};
+  std::vector<SubState> st(kThreads);
+  for (auto& s : st) sub_state_clear(s);
+  std::vector<float4> spec(kPairs);
+  std::vector<float> ss_ref(kThreads, 0.f), ss_sub(kThreads, 0.f);
+
+  const int nblk = (S + L - 1) / L;
+  for (int blk = 0; blk < nblk; ++blk) {
+    const int j0 = blk * L, i0 = j0 + o_t;
+    if (i0 >= R || i0 + kP <= 0) continue;  // block pruning, as the host planner does
+    BlockSource rs;
+    rs.src = ref.data() + i0;
+    rs.t_lo = i0 < 0 ? -i0 : 0;
+    rs.t_hi = (R - i0) < kP ? (R - i0) : kP;
+    forward_all(buf.data(), t, rs, ss_ref.data());
+    for (int tid = 0; tid < kThreads; ++tid) spec_store(buf.data(), t, tid, spec.data());
+    BlockSource bs;
+    bs.src = sub.data() + j0;
+    bs.t_lo = 0;
+    bs.t_hi = (S - j0) < L ? (S - j0) : L;
+    forward_all(buf.data(), t, bs, ss_sub.data());
+    for (int tid = 0; tid < kThreads; ++tid) sub_accumulate(st[tid], buf.data(), t, tid, spec.data());
+  }
+  for (int tid = 0; tid < kThreads; ++tid) sub_retangle_store(st[tid], buf.data(), t, tid);
+  for (int tid = 0; tid < kThreads; ++tid) inverse_passes_1(buf.data(), tid);
+  for (int tid = 0; tid < kThreads; ++tid) inverse_passes_2(buf.data(), t, tid);
+  for (int tid = 0; tid < kThreads; ++tid) inverse_passes_3(buf.data(), t, tid);
+  for (int tid = 0; tid < kThreads; ++tid) inverse_passes_4(buf.data(), t, tid);
+  std::vector<float> out(W + 2);
+  for (int m = 0; m < W; ++m) out[m] = window_value(buf.data(), m);
+  float es = 0.f, er = 0.f;
+  for (int tid = 0; tid < kThreads; ++tid) { es += ss_sub[tid]; er += ss_ref[tid]; }
+  out[W] = es;
+  out[W + 1] = er;
+  f = fopen(argv[2], "wb");
+  fwrite(out.data(), 4, W + 2, f);
+  fclose(f);
+  return 0;
+}

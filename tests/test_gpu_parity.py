@@ -1,0 +1,386 @@
+"""GPU parity tests (run on the B200 box): the CUDA path, called through the C ABI / the
+reference-shaped Python API, against the oracle and the committed golden fixtures.
+
+Bars: integer/index results bit-exact; correlation scores within 1e-5 relative (north_star)."""
+import math
+from datetime import timedelta
+
+import numpy as np
+import pytest
+
+import cases
+from oracle import aligner_oracle as ao
+from oracle import raster_oracle as ro
+from oracle import vad_oracle as vo
+
+pytestmark = pytest.mark.gpu
+
+SCORE_RTOL = 1e-5
+
+
+@pytest.fixture(scope="module")
+def handle():
+    from ffsubsync_b200 import _native
+    return _native.get_handle()
+
+
+def _score_ok(got, want):
+    if math.isinf(want) or math.isinf(got):
+        return got == want
+    return abs(got - want) <= SCORE_RTOL * max(abs(want), 1e-3) + 1e-6
+
+
+# =============================================================================== VAD (K1)
+
+@pytest.mark.parametrize("frame_rate", [16000, 48000, 44100, 8000, 32000])
+@pytest.mark.parametrize("label", [0.0, 0.5])
+def test_vad_matches_oracle(handle, frame_rate, label):
+    from ffsubsync_b200.speech_transformers import _make_energy_zcr_detector
+    fpw = vo.frames_per_window(frame_rate, 100)
+    rng = np.random.RandomState(frame_rate % 97)
+    cls = rng.randint(0, 3, 3000).astype(np.uint8)
+    pcm = vo.synth_pcm(cls, fpw, seed=11)
+    # perturb a few windows so energies land near the threshold and the band edges
+    pcm[: fpw * 50] = (pcm[: fpw * 50].astype(np.int32) * rng.uniform(0.02, 0.2)).astype(np.int16)
+    det = _make_energy_zcr_detector(100, frame_rate, label)
+    for cut in (len(pcm), len(pcm) - 7, fpw * 10 + 1, 3, 0):
+        chunk = pcm[:cut].tobytes()
+        want = vo.energy_zcr_detect(chunk, 100, frame_rate, label)
+        got = det(np.frombuffer(chunk, np.uint8)) if cut else det(b"")
+        assert got.dtype == np.float64 and np.array_equal(got, want), (frame_rate, cut)
+
+
+def test_vad_batch_ragged_and_thresholds(handle):
+    rng = np.random.RandomState(5)
+    fpw = 160
+    sigs = [vo.synth_pcm(rng.randint(0, 3, n).astype(np.uint8), fpw, seed=n)[: n * fpw - r]
+            for n, r in ((400, 0), (1, 0), (37, 5), (0, 0), (256, 159), (64, 1))]
+    sigs = [s if len(s) else np.zeros(0, np.int16) for s in sigs]
+    off = np.concatenate([[0], np.cumsum([len(s) for s in sigs])])
+    for thr, zlo, zhi in ((100000, -1, -1), (10, 0, 200), (100000, 2, 3), (5 * 10**7, 0, 160)):
+        out, out_off = handle.vad_energy_zcr(np.concatenate(sigs), off, 16000, 100, 0.25, thr, zlo, zhi)
+        for b, s in enumerate(sigs):
+            want = vo.energy_zcr_detect(s, 100, 16000, 0.25, thr, None if zlo < 0 else zlo,
+                                        None if zhi < 0 else zhi)
+            assert np.array_equal(out[out_off[b]:out_off[b + 1]].astype(np.float64), want), (b, thr)
+
+
+def test_vad_full_scale_samples(handle):
+    # int16 extremes: energy needs 64-bit accumulation (160 * 32768^2 > 2^32)
+    pcm = np.full(160 * 4, -32768, dtype=np.int16)
+    pcm[160:320] = 32767
+    pcm[320:480:2] = 32767
+    out, _ = handle.vad_energy_zcr(pcm, [0, len(pcm)], 16000, 100, 0.0, 100000, 0, 160)
+    assert np.array_equal(out.astype(np.float64), vo.energy_zcr_detect(pcm, 100, 16000, 0.0, 100000, 0, 160))
+
+
+def test_synth_pcm_matches_numpy_replay(handle):
+    cls = np.random.RandomState(2).randint(0, 3, 500).astype(np.uint8)
+    got = handle.synth_pcm(cls, len(cls), 160, seed=77)
+    assert np.array_equal(got, vo.synth_pcm(cls, 160, seed=77))
+
+
+def test_video_speech_transformer_chunk_protocol(handle):
+    """Chunked reads + progress callbacks as in the reference's loop (100 s per chunk)."""
+    from ffsubsync_b200.speech_transformers import VideoSpeechTransformer
+    fr = 16000
+    cls = np.random.RandomState(3).randint(0, 2, 25000).astype(np.uint8)  # 250 s
+    pcm = vo.synth_pcm(cls, 160, seed=5)
+    seen = []
+    t = VideoSpeechTransformer("energy_zcr", 100, fr, 0.0, progress_handler=seen.append)
+    t.fit(pcm.tobytes() + b"\x01")  # odd trailing byte is ignored
+    want = vo.energy_zcr_detect(pcm.tobytes(), 100, fr, 0.0)
+    assert np.array_equal(t.transform(), want)
+    assert [round(p.processed_seconds) for p in seen] == [100, 200, 250]
+    assert seen[-1].fraction == 1.0
+    with pytest.raises(ValueError, match="unknown vad"):
+        VideoSpeechTransformer("webrtc", 100, fr, 0.0).fit(b"\0\0")
+    with pytest.raises(ValueError, match="Unable to detect speech"):
+        VideoSpeechTransformer("energy", 100, fr, 0.0).fit(b"")
+
+
+# ========================================================================= rasteriser (K2, K7)
+
+def test_raster_matches_reference_fixtures(handle, golden, gf):
+    done = 0
+    for c in golden["raster"]:
+        starts, ends = cases.synthetic_cues(c["seed"], c["duration"])
+        out, off = handle.rasterize(starts, ends, None, [0, len(starts)], [c["ratio"]], 1, False, 100,
+                                    float(c["start_seconds"]))
+        assert len(out) == c["length"] == off[-1], c["ratio"]
+        levels, rs, re_ = cases.run_lengths(out)
+        assert rs == c["run_starts"] and re_ == c["run_stops"], (c["seed"], c["ratio"])
+        assert [np.float32(v) for v in c["levels"]] == [np.float32(v) for v in levels]
+        done += 1
+    assert done >= 30
+
+
+def test_raster_batch_k_ratios_and_boundaries(handle):
+    grid = cases.ratio_grid()
+    cue_sets = [cases.synthetic_cues(s, d) for s, d in ((1, 300.0), (2, 45.0), (3, 900.0))]
+    starts = np.concatenate([c[0] for c in cue_sets])
+    ends = np.concatenate([c[1] for c in cue_sets])
+    cue_off = np.concatenate([[0], np.cumsum([len(c[0]) for c in cue_sets])])
+    keep = (np.arange(len(starts)) % 7 != 3).astype(np.uint8)
+    out, off = handle.rasterize(starts, ends, keep, cue_off, grid, len(grid), False, 100, 0.0)
+    first, last = handle.first_last_nonzero(out, off)
+    for b, (st, en) in enumerate(cue_sets):
+        kb = keep[cue_off[b]:cue_off[b + 1]].astype(bool)
+        for k, r in enumerate(grid):
+            want, _, sf, ef = ro.rasterize(st, en, kb, 100, 0, r)
+            j = b * len(grid) + k
+            got = out[off[j]:off[j + 1]]
+            assert len(got) == len(want)
+            assert np.array_equal(got != 0, want != 0)
+            assert np.allclose(got[got != 0], np.float32(min(1.0 / r, 1.0)))
+            assert (first[j], last[j]) == (sf, ef)
+
+
+def test_subtitle_speech_transformer_kat(handle, golden, gf):
+    """tests/test_subtitles.py fake_srt timings through the reference-shaped classes."""
+    from ffsubsync_b200.sklearn_shim import make_pipeline
+    from ffsubsync_b200.speech_transformers import SubtitleSpeechTransformer
+    from ffsubsync_b200.subtitle_transformers import Cue, SubtitleScaler
+    k = golden["raster_kat"]
+    for c in k["cases"]:
+        subs = [Cue(timedelta(seconds=k["starts"][i]), timedelta(seconds=k["ends"][i]), k["contents"][i])
+                for i in c["cue_idx"]]
+        tr = SubtitleSpeechTransformer(sample_rate=c["sample_rate"], start_seconds=c["start_seconds"])
+        x = tr.fit(subs).transform()
+        assert x.dtype == np.float64 and len(x) == c["length"]
+        assert cases.run_lengths(x) == (c["levels"], c["run_starts"], c["run_stops"])
+        assert tr.max_time_ == gf(c["max_time"])
+        assert (tr.start_frame_, tr.end_frame_) == (c["start_frame"], c["end_frame"])
+    # scaler + transformer == fused oracle for a non-unit ratio, incl. the float64 level
+    starts, ends = cases.synthetic_cues(21, 120.0)
+    subs = [Cue(timedelta(seconds=s), timedelta(seconds=e), "hi") for s, e in zip(starts, ends)]
+    r = 25.0 / 24.0
+    pipe = make_pipeline(SubtitleScaler(r), SubtitleSpeechTransformer(100, 0, r))
+    got = pipe.fit_transform(subs)
+    want, max_time, sf, ef = ro.rasterize(starts, ends, None, 100, 0, r)
+    assert np.array_equal(got, want) and pipe[-1].num_frames == ef - sf
+
+
+# ============================================================================== aligner (K3-K5)
+
+def test_align_kats(handle, golden, gf):
+    from ffsubsync_b200.aligners import FFTAligner, MaxScoreAligner
+    for sub, ref, off in [("111001", "11001", -1), ("1001", "1001", 0), ("10010", "01001", 1)]:
+        assert FFTAligner().fit_transform(ref, sub) == off
+        assert MaxScoreAligner(FFTAligner).fit_transform(ref, sub)[0][1] == off
+        assert MaxScoreAligner(FFTAligner()).fit_transform(ref, sub)[0][1] == off
+    for c in golden["kats"]:
+        score, off = FFTAligner(c["mos"]).fit_transform(c["ref"], c["sub"], get_score=True)
+        want = gf(c["score"])
+        # exact ties (e.g. the all-negative case) are decided by float64 round-off in the
+        # reference; the GPU path breaks them like np.argmax on exact values
+        es, eo = ao.exact_align(c["ref"], c["sub"], c["mos"])
+        assert off == eo, c
+        assert _score_ok(score, want), (score, want)
+        if abs(es - want) < 1e-6 and off != c["offset"]:
+            pytest.fail("offset differs from the reference without a tie: %r" % (c,))
+
+
+def test_align_empty_inputs_raise(handle):
+    from ffsubsync_b200.aligners import FailedToFindAlignmentException, FFTAligner
+    for ref, sub in ((np.array([]), np.array([1, 0, 1])), (np.array([1, 0, 1]), np.array([])),
+                     (np.array([]), np.array([]))):
+        with pytest.raises(FailedToFindAlignmentException, match="empty speech data"):
+            FFTAligner().fit(ref, sub)
+
+
+def test_align_small_cases_batched(handle, golden, gf):
+    """240 random small cases (binary / two-level / float signals x mask regimes) in few calls."""
+    by_mos = {}
+    for c in golden["small"]:
+        by_mos.setdefault(c["mos"], []).append(c)
+    n_checked = n_tie = 0
+    for mos, group in by_mos.items():
+        refs, subs = [], []
+        for c in group:
+            ref, sub, m = cases.small_align_case(c["seed"])
+            refs.append(ref)
+            subs.append(sub)
+        ref_off = np.concatenate([[0], np.cumsum([len(r) for r in refs])])
+        sub_off = np.concatenate([[0], np.cumsum([len(s) for s in subs])])
+        score, offset, status = handle.align_batch(np.concatenate(refs), ref_off, np.concatenate(subs),
+                                                   sub_off, len(group), 1, mos)
+        for i, c in enumerate(group):
+            want = gf(c["score"])
+            # the GPU path is exact on the float32 values it is handed
+            es, eo = ao.exact_align(refs[i].astype(np.float32), subs[i].astype(np.float32), mos)
+            assert offset[i] == eo, (c, offset[i], eo)
+            assert _score_ok(score[i], es)
+            if offset[i] != c["offset"]:
+                # only legitimate when the reference's own maximum is a float64 near-tie
+                assert abs(ao.exact_score(refs[i], subs[i], c["offset"]) - es) < 1e-6, c
+                n_tie += 1
+            else:
+                assert _score_ok(score[i], want)
+            n_checked += 1
+    assert n_checked == 240 and n_tie < 40
+
+
+@pytest.mark.parametrize("n", [6000, 60000, 360000, 720000])
+def test_align_shifted_pairs(handle, golden, gf, n):
+    from ffsubsync_b200.aligners import FFTAligner
+    ref, sub = cases.shifted_pair(n)
+    for c in golden["shifted"]:
+        if c["n"] != n or (c["mos"] is None and n > 60000):
+            continue  # unmasked long inputs are covered once below (tiled path, slower)
+        score, off = FFTAligner(c["mos"]).fit_transform(ref, sub, get_score=True)
+        assert off == c["offset"] == -1234
+        assert score == n - 1234  # binary signals: the exact integer
+        assert _score_ok(score, gf(c["score"]))
+
+
+def test_align_unmasked_two_hours(handle, golden, gf):
+    """FFTAligner() with no mask on the 2 h config: every one of the 2^21 offsets is a candidate."""
+    from ffsubsync_b200.aligners import FFTAligner
+    ref, sub = cases.shifted_pair(720000)
+    score, off = FFTAligner().fit_transform(ref, sub, get_score=True)
+    want = [c for c in golden["shifted"] if c["n"] == 720000 and c["mos"] is None][0]
+    assert off == want["offset"] and score == 720000 - 1234
+
+
+def test_align_multi_segment_grid(handle, golden, golden_arrays, gf):
+    from ffsubsync_b200.aligners import FFTAligner, MaxScoreAligner
+    grid = cases.ratio_grid()
+    for ci, c in enumerate(golden["multi_segment"]):
+        n = int(golden_arrays["ms_sparse_len_%d" % ci])
+        sparse = np.unpackbits(golden_arrays["ms_sparse_%d" % ci])[:n].astype(float)
+        _, sub = cases.multi_segment_case(c["scale"], c["shift"])
+        subs = [cases.scaled_signal(sub, sf) for sf in grid]
+        m = MaxScoreAligner(FFTAligner, None, 100, 60).fit(sparse, subs)
+        for (got, _), want in zip(m._scores, c["per_ratio"]):
+            assert got[1] == want["offset"] and _score_ok(got[0], gf(want["score"]))
+        (score, off), pipe = m.transform()
+        k = [i for i, s in enumerate(subs) if s is pipe][0]
+        assert k == c["best"]["index"] and off == c["best"]["offset"]
+        assert grid[k] == pytest.approx(c["scale"], abs=1e-3)
+        assert off / 100.0 == pytest.approx(c["shift"], abs=0.05)
+
+
+def test_maxscore_grid_and_failure(handle, golden, gf):
+    from ffsubsync_b200.aligners import FailedToFindAlignmentException, FFTAligner, MaxScoreAligner
+    grid = cases.ratio_grid()
+    for c in golden["maxscore"]:
+        rng = np.random.RandomState(300 + c["seed"])
+        true_k = int(rng.randint(0, len(grid)))
+        shift = int(rng.randint(-3000, 3001))
+        base = (rng.rand(30000) > 0.55).astype(float)
+        ref = np.roll(cases.scaled_signal(base, grid[true_k]), shift)
+        ref = np.where(rng.rand(len(ref)) < 0.10, 1.0 - ref, ref)
+        subs = [cases.scaled_signal(base, r) * min(1.0 / r, 1.0) for r in grid]
+        m = MaxScoreAligner(FFTAligner, None, 100, 60).fit(ref, subs)
+        for (got, _), want in zip(m._scores, c["per_ratio"]):
+            assert got[1] == want["offset"] and _score_ok(got[0], gf(want["score"]))
+        (score, off), pipe = m.transform()
+        assert [i for i, s in enumerate(subs) if s is pipe][0] == c["best"]["index"]
+        assert off == c["best"]["offset"]
+    ref, sub = cases.shifted_pair(2000, 300)
+    m = MaxScoreAligner(FFTAligner(max_offset_samples=None), None, 100, 0.01).fit(ref, [sub])
+    with pytest.raises(FailedToFindAlignmentException, match="max-offset-seconds"):
+        m.transform()
+
+
+def test_reduce_ratios_kernel(handle):
+    score = np.array([5.0, 5.0, 4.0, 1.0, 9.0, 2.0, 3.0, 3.0, 3.0])
+    offset = np.array([1, 2, 0, 100, 200, 5, -7, 7, 8], dtype=np.int32)
+    bs, bo, bk = handle.reduce_ratios(score, offset, None, 3, 3, 10)
+    assert bk.tolist() == [0, 2, 0] and bo.tolist() == [1, 5, -7] and bs.tolist() == [5.0, 2.0, 3.0]
+    bs, bo, bk = handle.reduce_ratios(score, offset, None, 3, 3, None)
+    assert bk.tolist() == [0, 1, 0]
+    bs, bo, bk = handle.reduce_ratios(score[:3], np.array([50, 60, 70], np.int32), None, 1, 3, 10)
+    assert bk.tolist() == [-1]
+
+
+def test_gss_fit(handle, golden, gf):
+    """--gss: 17 sequential evaluations with the reference's ratios; same winner."""
+    from ffsubsync_b200.aligners import FFTAligner, MaxScoreAligner
+    want = golden["gss_fit"]
+    ref_full, sub = cases.multi_segment_case(25.0 / 24.0, 3.0)
+    evals = []
+
+    class Pipe:
+        def __init__(self, ratio):
+            self.ratio = ratio
+
+        def fit_transform(self, _):
+            return cases.scaled_signal(sub, self.ratio)
+
+    def maker(ratio):
+        evals.append(float(ratio))
+        return Pipe(ratio)
+
+    m = MaxScoreAligner(FFTAligner, None, 100, 60)
+    m.fit(ref_full, [maker])
+    (score, off), pipe = m.transform()
+    assert evals == want["evals"]
+    assert off == want["offset"] and pipe.ratio == want["ratio"] and _score_ok(score, gf(want["score"]))
+
+
+# ========================================================================= whole hot path, batch
+
+def _pair(seed, duration_s, ratio_k, delta, grid, fr=16000):
+    """Synthetic (PCM, cues) pair: the reference mask is the subtitle mask at grid[ratio_k] delayed
+    by delta frames with 10 % of the frames flipped."""
+    starts, ends = cases.synthetic_cues(seed, duration_s)
+    mask, _, _, _ = ro.rasterize(starts, ends, None, 100, 0, grid[ratio_k])
+    mask = (mask != 0)
+    n = int(duration_s * 100)
+    ref = np.zeros(n, dtype=bool)
+    src = np.arange(n) - delta
+    ok = (src >= 0) & (src < len(mask))
+    ref[ok] = mask[src[ok]]
+    rng = np.random.RandomState(seed + 1000)
+    ref ^= rng.rand(n) < 0.10
+    hiss = rng.rand(n) < 0.05
+    cls = np.where(ref, 1, np.where(hiss, 2, 0)).astype(np.uint8)
+    return cls, starts, ends
+
+
+def test_sync_batch_small_vs_oracle(handle):
+    grid = [1.0, 24 / 23.976, 25 / 24.0, 23.976 / 24, 24 / 25.0]
+    fpw = 160
+    spec = [(31, 240.0, 0, 250), (32, 300.0, 2, -700), (33, 180.0, 4, 0), (34, 200.0, 1, 1234)]
+    cls_all, pcm_off, cs, ce, cue_off = [], [0], [], [], [0]
+    for seed, dur, k, delta in spec:
+        cls, st, en = _pair(seed, dur, k, delta, grid)
+        cls_all.append(cls)
+        pcm_off.append(pcm_off[-1] + len(cls) * fpw)
+        cs.append(st)
+        ce.append(en)
+        cue_off.append(cue_off[-1] + len(st))
+    cls_cat = np.concatenate(cls_all)
+    pcm = vo.synth_pcm(cls_cat, fpw, seed=9)
+    bs, bo, bk, a_s, a_o = handle.sync_batch(
+        pcm, pcm_off, 16000, 100, 0.0, 100000, -1, -1, np.concatenate(cs), np.concatenate(ce), None,
+        cue_off, grid, 0.0, 6000, want_all=True)
+    for b, (seed, dur, k, delta) in enumerate(spec):
+        ref_sig = vo.energy_zcr_detect(pcm[pcm_off[b]:pcm_off[b + 1]], 100, 16000, 0.0)
+        subs = [ro.rasterize(cs[b], ce[b], None, 100, 0, r)[0] for r in grid]
+        results = [ao.fft_align(ref_sig, s, 6000) for s in subs]
+        for kk, (ws, wo) in enumerate(results):
+            assert a_o[b * len(grid) + kk] == wo
+            assert _score_ok(a_s[b * len(grid) + kk], ws)
+        wk = ao.max_score_select(results, 6000)
+        assert (bk[b], bo[b]) == (wk, results[wk][1]) == (k, delta)
+        assert _score_ok(bs[b], results[wk][0])
+
+
+def test_sync_two_hour_pair_recovers_offset(handle):
+    """BASELINE config 2: synthetic 2 h PCM at 16 kHz + shifted cues, VAD + alignment end to end.
+    Full-size check through domain properties: the known offset/ratio are recovered, the score is
+    the exact count of agreeing minus disagreeing frames (binary signals)."""
+    grid = [1.0, 24 / 23.976, 25 / 24.0, 23.976 / 24, 24 / 25.0]
+    cls, st, en = _pair(77, 7200.0, 0, -2718, grid)
+    pcm = handle.synth_pcm(cls, len(cls), 160, seed=123)
+    assert len(pcm) == 115200000
+    bs, bo, bk, a_s, a_o = handle.sync_batch(pcm, [0, len(pcm)], 16000, 100, 0.0, 100000, -1, -1, st, en,
+                                             None, [0, len(st)], grid, 0.0, 6000, want_all=True)
+    assert (bk[0], bo[0]) == (0, -2718)
+    ref_sig = (cls == 1).astype(float)
+    sub = ro.rasterize(st, en, None, 100, 0, 1.0)[0]
+    assert bs[0] == ao.exact_score(ref_sig, sub, -2718)
+    assert np.all(a_s[1:] < bs[0])

@@ -1,0 +1,206 @@
+"""CPU suite for the host side: the C-ABI library loads and exports every symbol the header
+declares (no compute without a GPU), the host logic (pipeline shim, golden-section search,
+metadata filter, length helper), the CPU emulation of the correlation kernels, and the
+"fail loudly, no CPU fallback" rule."""
+import os
+import re
+import struct
+import subprocess
+import sys
+from datetime import timedelta
+
+import numpy as np
+import pytest
+
+import cases
+from conftest import ROOT
+from oracle import aligner_oracle as ao
+from oracle import gss_oracle as go
+from oracle import raster_oracle as ro
+
+
+@pytest.fixture(scope="module")
+def built():
+    sys.path.insert(0, ROOT)
+    import __graft_entry__ as ge
+    ge.build()
+    return ge
+
+
+def test_library_exports_every_header_symbol(built):
+    import ctypes
+    from ffsubsync_b200 import _native
+    header = open(os.path.join(ROOT, "include", "ffsubsync_b200.h")).read()
+    declared = sorted(set(re.findall(r"\b(b2_[a-z0-9_]+)\s*\(", header)))
+    assert declared == sorted(_native.EXPORTS)
+    lib = ctypes.CDLL(_native.LIB_PATH)
+    for name in declared:
+        assert hasattr(lib, name), name
+    assert _native.load().b2_version() == 100
+    # every declaration cites the reference interface it replaces
+    assert header.count("ffsubsync/") >= 8
+
+
+def test_pure_host_entry_points(built):
+    from ffsubsync_b200 import _native
+    lib = _native.load()
+    assert lib.b2_vad_frames_per_window(16000, 100) == 160
+    assert lib.b2_vad_frames_per_window(44100, 100) == 441
+    assert lib.b2_vad_num_windows(115200000, 16000, 100) == 720000
+    assert lib.b2_vad_num_windows(161, 16000, 100) == 2
+    # b2_rasterize_lengths == int(max_end*sr)+2 of the reference, for awkward ratios
+    starts, ends = cases.synthetic_cues(15, 7200.0)
+    ratios = np.array(cases.ratio_grid() + [0.9, 1.1, 0.976393])
+    lengths = np.empty(len(ratios), dtype=np.int64)
+    off = np.array([0, len(ends)], dtype=np.int64)
+    st = lib.b2_rasterize_lengths(ends.ctypes.data, off.ctypes.data, 1, ratios.ctypes.data, len(ratios), 0,
+                                  100, lengths.ctypes.data)
+    assert st == 0
+    for r, n in zip(ratios, lengths):
+        assert n == len(ro.rasterize(starts, ends, None, 100, 0, r)[0])
+
+
+def test_no_cpu_fallback_without_gpu(built):
+    """On a box without a CUDA device every compute entry point must raise, not fall back."""
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    from ffsubsync_b200 import _native
+    from ffsubsync_b200.aligners import FFTAligner
+    from ffsubsync_b200.speech_transformers import _make_energy_zcr_detector
+    with pytest.raises(_native.NativeError):
+        _native.Handle(0)
+    with pytest.raises(_native.NativeError):
+        FFTAligner().fit([1, 0, 1], [1, 0])
+    with pytest.raises(_native.NativeError):
+        _make_energy_zcr_detector(100, 16000, 0.0)
+    src = open(os.path.join(ROOT, "ffsubsync_b200", "aligners.py")).read() + \
+        open(os.path.join(ROOT, "ffsubsync_b200", "speech_transformers.py")).read() + \
+        open(os.path.join(ROOT, "ffsubsync_b200", "_native.py")).read()
+    assert "oracle" not in src.replace("oracle/vad_oracle.py", "")  # product never imports the oracle
+
+
+def test_empty_input_raises_before_the_gpu_is_needed(built):
+    from ffsubsync_b200.aligners import FailedToFindAlignmentException, FFTAligner
+    with pytest.raises(FailedToFindAlignmentException, match="empty speech data"):
+        FFTAligner().fit(np.array([]), np.array([1, 0, 1]))
+
+
+# ------------------------------------------------------------------------------ pipeline shim
+
+class _Add:
+    def __init__(self, k):
+        self.k, self.fitted = k, 0
+
+    def fit(self, X, y=None, **kw):
+        self.fitted += 1
+        self.kw = kw
+        return self
+
+    def transform(self, X):
+        return X + self.k
+
+
+def test_pipeline_surface():
+    from ffsubsync_b200.sklearn_shim import Pipeline, TransformerMixin, make_pipeline
+    a, b, c = _Add(1), _Add(10), _Add(100)
+    pipe = Pipeline([("a", a), ("skip", None), ("b", b), ("c", c)])
+    assert pipe.fit(0) is pipe and (a.fitted, b.fitted, c.fitted) == (1, 1, 1)
+    assert pipe.transform(0) == 111            # property returning a callable
+    assert pipe.fit_transform(1) == 112
+    assert pipe[-1] is c and pipe["b"] is b and pipe.named_steps["a"] is a and len(pipe) == 4
+    assert isinstance(pipe[1:], Pipeline) and pipe.steps[-1][1] is c
+    pipe.fit(0, b__flag=3)
+    assert b.kw == {"flag": 3}
+    with pytest.raises(ValueError, match="does not accept"):
+        pipe.fit(0, flag=1)
+    with pytest.raises(TypeError):
+        Pipeline([("x", object()), ("y", _Add(1))])
+    mp = make_pipeline(_Add(1), _Add(2), "passthrough")
+    assert [n for n, _ in mp.steps] == ["_add-1", "_add-2", "passthrough"]
+    assert mp.fit_transform(0) == 3
+
+    class T(TransformerMixin):
+        def fit(self, X, y="none", **kw):
+            self.got = (X, y, kw)
+            return self
+
+        def transform(self, X):
+            return self.got
+
+    assert T().fit_transform(1) == (1, "none", {})
+    assert T().fit_transform(1, 2, get_score=True) == (1, 2, {"get_score": True})
+
+
+def test_gss_matches_oracle_trace(golden):
+    from ffsubsync_b200.golden_section_search import gss
+    calls = []
+    interval = gss(lambda x, last: calls.append((x, last)) or (x - 1.0417) ** 2, 0.9, 1.1)
+    want = golden["gss_quadratic"]
+    assert [list(c) for c in calls] == [list(c) for c in want["calls"]]
+    assert list(interval) == want["interval"]
+    assert gss(lambda x: x * x, 1.0, 1.00001) == (1.0, 1.00001)
+
+
+def test_metadata_filter_and_constants(golden):
+    from ffsubsync_b200 import constants
+    from ffsubsync_b200.speech_transformers import _is_metadata
+    for c in golden["metadata"]:
+        assert _is_metadata(c["content"], c["edge"]) == c["is_metadata"], c
+    assert constants.SAMPLE_RATE == 100 and constants.DEFAULT_MAX_OFFSET_SECONDS == 60
+    got = constants.framerate_ratios_to_try()
+    assert [float(x) for x in got] == [float(x) for x in cases.ratio_grid()[1:]]
+    assert constants.framerate_ratios_to_try(gss=True)[-1] is None
+    assert constants.framerate_ratios_to_try(no_fix_framerate=True) == []
+
+
+def test_scaler_roundtrip(golden):
+    from ffsubsync_b200.subtitle_transformers import Cue, SubtitleScaler
+    for c in golden["scale_roundtrip"][:100]:
+        subs = [Cue(timedelta(seconds=c["t"]), timedelta(seconds=c["t"] + 1), "x")]
+        out = SubtitleScaler(c["r"]).fit(subs).transform()
+        assert out[0].start.total_seconds() == c["scaled"] and out[0].content == "x"
+
+
+# --------------------------------------------------------- CPU emulation of the FFT kernel chain
+
+def _emulate(ref, sub, o_t, W):
+    P = 32768
+    L = P - (W | 1) + 1
+    tmp = os.path.join(ROOT, "tests", "host_emul")
+    fin, fout = os.path.join(tmp, "_in.bin"), os.path.join(tmp, "_out.bin")
+    with open(fin, "wb") as f:
+        f.write(struct.pack("5i", len(ref), len(sub), o_t, W, L))
+        f.write(np.asarray(ref, np.float32).tobytes())
+        f.write(np.asarray(sub, np.float32).tobytes())
+    subprocess.check_call([os.path.join(tmp, "corr_emul"), fin, fout])
+    out = np.fromfile(fout, dtype=np.float32)
+    os.remove(fin)
+    os.remove(fout)
+    return out[:W].astype(np.float64), float(out[W]), float(out[W + 1])
+
+
+def _direct(ref, sub, o_t, W):
+    r, s = 2 * np.asarray(ref, np.float64) - 1, 2 * np.asarray(sub, np.float64) - 1
+    n = 1 << int(np.ceil(np.log2(len(r) + len(s))))
+    full = np.fft.irfft(np.conj(np.fft.rfft(s, n)) * np.fft.rfft(r, n), n)
+    return np.array([full[o % n] if -len(s) < o < len(r) else 0.0 for o in range(o_t, o_t + W)])
+
+
+@pytest.mark.parametrize("R,S,o_t,W", [(11, 6, -6, 16), (300, 250, -20, 41), (60000, 61000, -5999, 12000),
+                                       (50000, 70000, -16000, 16385), (40000, 40000, 20000, 16385)])
+def test_kernel_chain_emulation(built, R, S, o_t, W):
+    """The exact __host__ __device__ kernel code, run thread by thread on the CPU, reproduces the
+    float64 correlation within the round-off bound the candidate selection assumes."""
+    rng = np.random.RandomState(R + S)
+    ref = (rng.rand(R) > 0.5).astype(np.float32)
+    sub = (rng.rand(S) > 0.5).astype(np.float32) * np.float32(0.96)
+    if R > 1000:
+        k = min(R, S) - 1234
+        sub[1234:1234 + k] = ref[:k] * np.float32(0.96)
+    got, es, er = _emulate(ref, sub, o_t, W)
+    want = _direct(ref, sub, o_t, W)
+    err = np.abs(got - want).max()
+    bound = 2.0 ** -24 * np.sqrt(es * er)
+    assert err <= 8 * bound + 1e-6, (err, bound)          # selection uses 64 * bound
+    assert np.argmax(got) == np.argmax(want)
