@@ -1,0 +1,382 @@
+#!/usr/bin/env python
+"""bench.py - alignments/sec of the ffsubsync hot path on B200 (BASELINE.json metric).
+
+A "step" = one pass of the whole hot path (VAD on 2 h of 16 kHz PCM -> K=5 ratio candidates
+rasterised -> windowed FFT correlation + exact re-score -> max over ratios) over one batch of
+synthetic pairs per GPU.  `value` counts whole-job alignments (pairs) per second with the PCM
+already resident in HBM; `e2e` is the same call through the C ABI with HOST (pinned) buffers,
+H2D/D2H inside the timed region.  `--impl reference` times the reference's own CPU algorithm
+(numpy complex128 FFT aligner + the numpy restatement of the detector, oracle/) on the host
+cores of the same box.
+
+    python bench.py --gpus 1 --steps 5 --warmup 3
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 \
+        --master-port 29500 bench.py --gpus 8 --steps 5 --warmup 3
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "alignments/sec (2h@100Hz signals)"
+UNIT = "alignments/s"
+DURATION_S = 7200.0
+FRAME_RATE = 16000
+FPW = 160
+SAMPLE_RATE = 100
+MAX_OFFSET_SECONDS = 60
+# compulsory bytes per 2 h pair
+BYTES_VAD = 2 * FRAME_RATE * int(DURATION_S) + 4 * SAMPLE_RATE * int(DURATION_S)   # 233 280 000
+
+
+def bytes_align(k):
+    return 4 * 720000 * (1 + k) + 8 * k
+
+
+def measured_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        with open(p) as fh:
+            return float(json.load(fh)["hbm_gbs"]), "measured (MEASURED_PEAKS.json, copy bandwidth)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled during the timed region."""
+
+    FIELDS = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+              "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+              "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.FIELDS,
+                 "--format=csv,noheader,nounits", "-lms", "100"],
+                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._pump, daemon=True).start()
+        except OSError:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.rows.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm, smax, reasons = [], [], set()
+        for row in self.rows:
+            f = [x.strip() for x in row.split(",")]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[0]))
+                smax.append(float(f[1]))
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        busy = [c for c in sm if c > 0]
+        return {"sm_mhz": float(np.median(busy)) if busy else None,
+                "sm_max_mhz": max(smax) if smax else None, "samples": len(sm), "reasons": sorted(reasons)}
+
+
+# ------------------------------------------------------------------------------------ GPU arm
+
+def run_gpu(args):
+    import torch
+    from ffsubsync_b200 import _native, distributed
+    from ffsubsync_b200.batch import BatchSynchronizer
+    from ffsubsync_b200.synth import BENCH_RATIOS, make_pairs
+
+    rank, world, local_rank = distributed.init_from_env("nccl")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    ratios = BENCH_RATIOS[: args.ratios] if args.ratios <= len(BENCH_RATIOS) else None
+    if ratios is None:
+        from ffsubsync_b200.constants import FRAMERATE_RATIOS
+        r = np.array(FRAMERATE_RATIOS)
+        ratios = [1.0] + list(np.concatenate([r, 1.0 / r]))[: args.ratios - 1]
+    K = len(ratios)
+    B = args.pairs                      # per GPU (weak scaling)
+    bs = BatchSynchronizer(ratios, FRAME_RATE, SAMPLE_RATE, 0.0, max_offset_seconds=MAX_OFFSET_SECONDS,
+                           device=local_rank)
+    h = bs.handle
+    stream = torch.cuda.current_stream()
+    bs.use_torch_stream()
+
+    # ---- synthetic inputs (untimed): masks on the host, PCM synthesised on the device --------
+    seeds = [13 + rank * B + b for b in range(B)]
+    pairs = make_pairs(seeds, DURATION_S, ratios, handle=h)
+    n_win = int(pairs.win_off[-1])
+    cls_d = torch.from_numpy(pairs.window_class).to(dev)
+    pcm_d = torch.empty(n_win * FPW, dtype=torch.int16, device=dev)
+    h.synth_pcm(cls_d.data_ptr(), n_win, FPW, 1234 + rank, out=pcm_d.data_ptr(), memspace=_native.B2_DEVICE)
+    del cls_d
+    pcm_off = pairs.win_off * FPW
+    out = {"best_score": torch.empty(B, dtype=torch.float64, device=dev),
+           "best_offset": torch.empty(B, dtype=torch.int32, device=dev),
+           "best_k": torch.empty(B, dtype=torch.int32, device=dev)}
+    packed = torch.empty((B, 3), dtype=torch.float64, device=dev)
+
+    def step():
+        bs.sync_device(pcm_d, pcm_off, pairs.cue_start, pairs.cue_end, pairs.cue_off, out=out)
+        if world > 1:  # the only exchange of the path: per-pair results to rank 0 (NCCL)
+            packed[:, 0] = out["best_score"]
+            packed[:, 1] = out["best_offset"].to(torch.float64)
+            packed[:, 2] = out["best_k"].to(torch.float64)
+            return distributed.gather_pair_results(packed, B * world, rank, world)
+        return None
+
+    for _ in range(args.warmup):
+        step()
+    torch.cuda.synchronize()
+    ok = bool((out["best_offset"].cpu().numpy() == pairs.true_offset).all()
+              and (out["best_k"].cpu().numpy() == pairs.true_k).all())
+
+    sampler = ClockSampler(local_rank)
+    if world > 1:
+        torch.distributed.barrier()
+    torch.cuda.synchronize()
+    if rank == 0:
+        sampler.start()
+    launches0 = h.launch_count
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev0.record(stream)
+    for _ in range(args.steps):
+        step()
+    ev1.record(stream)
+    torch.cuda.synchronize()
+    if world > 1:
+        torch.distributed.barrier()
+    elapsed_ms = distributed.max_over_ranks(ev0.elapsed_time(ev1), dev)
+    launches = h.launch_count - launches0
+    clocks = sampler.stop() if rank == 0 else None
+
+    # ---- per-stage device times (CUDA events on the launching stream), rank 0 only -------------
+    stages, roofline, e2e, cpu_base = {}, None, None, None
+    peak, peak_src = measured_peaks()
+    if rank == 0:
+        ref_off = pairs.win_off
+        ref_sig = torch.empty(n_win, dtype=torch.float32, device=dev)
+
+        def timed(fn, reps):
+            fn()
+            torch.cuda.synchronize()
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record(stream)
+            for _ in range(reps):
+                fn()
+            b.record(stream)
+            torch.cuda.synchronize()
+            return a.elapsed_time(b) / reps
+
+        vad_ms = timed(lambda: h.vad_energy_zcr(pcm_d.data_ptr(), pcm_off, FRAME_RATE, SAMPLE_RATE, 0.0, 100000,
+                                                out=ref_sig.data_ptr(), memspace=_native.B2_DEVICE), args.steps)
+        lengths = h.rasterize_lengths(pairs.cue_end, pairs.cue_off, ratios, K, False, SAMPLE_RATE)
+        sub_off = np.concatenate([[0], np.cumsum(lengths)]).astype(np.int64)
+        sub_sig = torch.empty(int(sub_off[-1]), dtype=torch.float32, device=dev)
+        ras_ms = timed(lambda: h.rasterize(pairs.cue_start, pairs.cue_end, None, pairs.cue_off, ratios, K, False,
+                                           SAMPLE_RATE, 0.0, out=sub_sig.data_ptr(), out_off=sub_off,
+                                           memspace=_native.B2_DEVICE), args.steps)
+        sc = torch.empty(B * K, dtype=torch.float64, device=dev)
+        of = torch.empty(B * K, dtype=torch.int32, device=dev)
+        st = torch.empty(B * K, dtype=torch.int32, device=dev)
+        ali_ms = timed(lambda: h.align_batch(ref_sig.data_ptr(), ref_off, sub_sig.data_ptr(), sub_off, B, K,
+                                             MAX_OFFSET_SECONDS * SAMPLE_RATE, score=sc.data_ptr(),
+                                             offset=of.data_ptr(), status=st.data_ptr(),
+                                             memspace=_native.B2_DEVICE), args.steps)
+        stages = {"vad_ms": vad_ms, "rasterize_ms": ras_ms, "align_ms": ali_ms}
+        achieved = BYTES_VAD * B / (vad_ms * 1e-3) / 1e9
+        roofline = {"kernel": "vad_energy_zcr_kernel", "bound": "hbm", "achieved": achieved, "peak": peak,
+                    "unit": "GB/s", "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+                    "algorithmic_bytes_per_launch": BYTES_VAD * B,
+                    "whole_path": {"achieved": (BYTES_VAD + bytes_align(K)) * B * args.steps
+                                   / (elapsed_ms * 1e-3) / 1e9 if world == 1 else None,
+                                   "unit": "GB/s (algorithmic bytes of VAD + align over the step time)"}}
+        if roofline["whole_path"]["achieved"]:
+            roofline["whole_path"]["frac"] = roofline["whole_path"]["achieved"] / peak
+        del ref_sig, sub_sig
+
+        # ---- e2e: same call, HOST buffers (pinned), H2D + D2H inside the timed region ------------
+        Be = min(args.e2e_pairs, B)
+        n_e = int(pairs.win_off[Be]) * FPW
+        pcm_h = torch.empty(n_e, dtype=torch.int16, pin_memory=True)
+        pcm_h.copy_(pcm_d[:n_e])
+        torch.cuda.synchronize()
+        cue_hi = int(pairs.cue_off[Be])
+        e_args = (pcm_h.numpy(), pcm_off[: Be + 1], pairs.cue_start[:cue_hi], pairs.cue_end[:cue_hi],
+                  pairs.cue_off[: Be + 1])
+        for _ in range(2):
+            res = bs.sync_host(*e_args)
+        t0 = time.perf_counter()
+        for _ in range(args.steps):
+            res = bs.sync_host(*e_args)   # synchronises before returning: results are on the host
+        e_s = (time.perf_counter() - t0) / args.steps
+        ok = ok and bool((res[1] == pairs.true_offset[:Be]).all())
+        e2e = {"value": Be / e_s, "unit": UNIT, "pairs_per_step": Be,
+               "h2d_bytes_per_step": int(n_e * 2 + cue_hi * 16 + (Be + 1) * 16 + K * 8),
+               "d2h_bytes_per_step": int(Be * 16), "ms_per_step": e_s * 1e3,
+               "note": "single GPU (rank 0), PCIe H2D of the PCM is the bound"}
+        del pcm_h
+        if world == 1 and not args.no_cpu_baseline:
+            cpu_base = cpu_baseline_sample(K, ratios, budget_pairs=None)
+
+    if rank == 0:
+        total_pairs = B * world * args.steps
+        line = {
+            "metric": METRIC, "value": total_pairs / (elapsed_ms * 1e-3), "unit": UNIT, "n_gpus": world,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": elapsed_ms / args.steps,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "int64 VAD; f32 FFT nomination + f64 exact re-score", "data": "synthetic",
+            "config": {"workload": "BASELINE configs[2] with the VAD of configs[1]: batch of 2 h pairs per GPU, "
+                                   "16 kHz mono s16le PCM -> energy/ZCR VAD -> MaxScoreAligner over K ratios, "
+                                   "max_offset_seconds=60", "pairs_per_gpu": B, "ratios": K,
+                       "signal_frames": 720000, "pcm_samples_per_pair": 115200000,
+                       "l2_policy": "inputs (%.1f GB PCM per GPU) are far larger than the 126 MB L2"
+                                    % (B * 0.2304), "parallelism": "pairs block-sharded, dp%d" % world},
+            "verified_offsets": ok, "gpu_launches": int(launches), "clocks": clocks, "stages_ms": stages,
+            "roofline": roofline, "e2e": e2e, "cpu_baseline": cpu_base,
+        }
+        print(json.dumps(line))
+    if world > 1:
+        torch.distributed.barrier()
+        torch.distributed.destroy_process_group()
+
+
+# ------------------------------------------------------------------------- CPU / reference arm
+
+_CPU_STATE = {}
+
+
+def _cpu_worker(job):
+    """One 2 h pair through the reference's algorithm on one host core: the numpy restatement of
+    the detector in 100 s chunks (speech_transformers.py:710-746), the per-ratio scaler +
+    rasteriser and the complex128 FFT aligner (aligners.py:50-80), max over ratios."""
+    from oracle import aligner_oracle as ao
+    from oracle import raster_oracle as ro
+    from oracle import vad_oracle as vo
+    pcm, starts, ends, ratios = _CPU_STATE["pcm"], _CPU_STATE["starts"], _CPU_STATE["ends"], _CPU_STATE["ratios"]
+    chunk = 2 * FRAME_RATE // SAMPLE_RATE * 10000 // 2
+    ref = np.concatenate([vo.energy_zcr_detect(pcm[i:i + chunk], SAMPLE_RATE, FRAME_RATE, 0.0)
+                          for i in range(0, len(pcm), chunk)])
+    subs = [ro.rasterize(starts, ends, None, SAMPLE_RATE, 0, r)[0] for r in ratios]
+    (score, off), k = ao.max_score_align(ref, subs, SAMPLE_RATE, MAX_OFFSET_SECONDS)
+    return off, k
+
+
+def _cpu_setup(ratios):
+    from oracle import raster_oracle as ro
+    from oracle import vad_oracle as vo
+    if "pcm" in _CPU_STATE:
+        return
+    starts, ends = ro.synthetic_cues(13, DURATION_S)
+    mask = ro.rasterize(starts, ends, None, SAMPLE_RATE, 0, 1.0)[0] != 0
+    n = int(DURATION_S * SAMPLE_RATE)
+    ref = np.zeros(n, dtype=bool)
+    src = np.arange(n) - 1234
+    okm = (src >= 0) & (src < len(mask))
+    ref[okm] = mask[src[okm]]
+    ref ^= np.random.RandomState(1).rand(n) < 0.10
+    _CPU_STATE.update(pcm=vo.synth_pcm(ref.astype(np.uint8), FPW, seed=7), starts=starts, ends=ends,
+                      ratios=list(ratios), expect=1234)
+
+
+def cpu_pass(n_pairs, cores):
+    import multiprocessing as mp
+    t0 = time.perf_counter()
+    if cores == 1:
+        res = [_cpu_worker(i) for i in range(n_pairs)]
+    else:
+        with mp.get_context("fork").Pool(cores) as pool:
+            res = pool.map(_cpu_worker, range(n_pairs), chunksize=1)
+    dt = time.perf_counter() - t0
+    assert all(r[0] == _CPU_STATE["expect"] for r in res), res
+    return n_pairs / dt, dt
+
+
+def cpu_baseline_sample(K, ratios, budget_pairs=None):
+    for v in ("OMP_NUM_THREADS", "MKL_NUM_THREADS", "OPENBLAS_NUM_THREADS"):
+        os.environ[v] = "1"
+    cores = os.cpu_count() or 1
+    used = max(1, min(cores, 32))
+    _cpu_setup(ratios)
+    n_pairs = budget_pairs or used
+    rate, dt = cpu_pass(n_pairs, used)
+    return {"value": rate, "unit": UNIT, "cores": used, "host_cores": cores, "kind": "port",
+            "sample": "%d two-hour pairs (one per worker process), K=%d ratios, VAD + aligner, %.1f s wall"
+                      % (n_pairs, K, dt)}
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    from ffsubsync_b200.synth import BENCH_RATIOS
+    ratios = BENCH_RATIOS[: args.ratios]
+    K = len(ratios)
+    for v in ("OMP_NUM_THREADS", "MKL_NUM_THREADS", "OPENBLAS_NUM_THREADS"):
+        os.environ[v] = "1"
+    cores = os.cpu_count() or 1
+    used = max(1, min(cores, 32))
+    _cpu_setup(ratios)
+    per_step = used
+    for _ in range(min(args.warmup, 1)):   # one warm-up pass is enough for a CPU pool; bounded runtime
+        cpu_pass(per_step, used)
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        cpu_pass(per_step, used)
+    dt = time.perf_counter() - t0
+    value = per_step * args.steps / dt
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "int64 VAD; complex128 FFT",
+        "data": "synthetic",
+        "config": {"workload": "same as the GPU arm: 2 h pairs, 16 kHz PCM -> energy/ZCR detector (numpy "
+                               "restatement) -> FFTAligner (numpy complex128, aligners.py:50-80) over K ratios, "
+                               "max_offset_seconds=60", "pairs_per_step": per_step, "ratios": K},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": used, "host_cores": cores, "kind": "port",
+                         "sample": "%d two-hour pairs per step, one per worker process" % per_step},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "note": "the reference is pure Python and cannot travel to the GPU box; this is the oracle port of "
+                "its algorithm (pinned to the reference by tests/golden) on all host cores",
+    }
+    print(json.dumps(line))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--pairs", type=int, default=int(os.environ.get("B2_BENCH_PAIRS", "64")),
+                    help="2 h pairs per GPU per step")
+    ap.add_argument("--ratios", type=int, default=5)
+    ap.add_argument("--e2e-pairs", type=int, default=4)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_gpu(args)
+
+
+if __name__ == "__main__":
+    main()

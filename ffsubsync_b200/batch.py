@@ -1,0 +1,72 @@
+"""Batch front end of the hot path: many (video, subtitle) pairs per call.
+
+``BatchSynchronizer.sync_device`` keeps everything resident in HBM (PCM in, per-pair
+``(score, offset, ratio index)`` out) and launches on torch's current CUDA stream, so callers
+can time it with torch.cuda.Event and chain it with NCCL collectives (ffsubsync_b200.distributed).
+``sync_host`` is the same call with host buffers (numpy / pinned tensors): the C library copies
+the PCM in, runs the identical kernels and copies the results out.
+
+This is what ``ffs ref.mkv -i in.srt`` does per pair in the reference - VideoSpeechTransformer.fit
+(ffsubsync/ffsubsync.py:637) followed by MaxScoreAligner over the ratio grid (:196-235) - for a
+batch, with the subtitle scaling + rasterisation fused into one kernel.
+"""
+from typing import Optional, Sequence
+
+import numpy as np
+
+from . import _native
+from .constants import DEFAULT_ENERGY_THRESHOLD, DEFAULT_MAX_OFFSET_SECONDS, SAMPLE_RATE
+
+
+class BatchSynchronizer:
+    def __init__(self, ratios: Sequence[float], frame_rate: int = 16000, sample_rate: int = SAMPLE_RATE,
+                 non_speech_label: float = 0.0, energy_threshold: int = DEFAULT_ENERGY_THRESHOLD,
+                 z_lo: int = -1, z_hi: int = -1, start_seconds: float = 0.0,
+                 max_offset_seconds: Optional[float] = DEFAULT_MAX_OFFSET_SECONDS,
+                 device: Optional[int] = None) -> None:
+        self.ratios = np.ascontiguousarray(ratios, dtype=np.float64)
+        self.frame_rate = frame_rate
+        self.sample_rate = sample_rate
+        self.non_speech_label = non_speech_label
+        self.energy_threshold = energy_threshold
+        self.z_lo, self.z_hi = z_lo, z_hi
+        self.start_seconds = start_seconds
+        # MaxScoreAligner.__init__ (ffsubsync/aligners.py:98-101)
+        self.max_offset_samples = None if max_offset_seconds is None else abs(int(max_offset_seconds * sample_rate))
+        self.handle = _native.get_handle(device)
+
+    def use_torch_stream(self) -> None:
+        """Launch on torch's current stream (so torch events / NCCL ops order against our kernels)."""
+        import torch
+        self.handle.set_stream(torch.cuda.current_stream().cuda_stream)
+
+    def sync_device(self, pcm, pcm_off, cue_start, cue_end, cue_off, cue_keep=None, out=None, all_out=None):
+        """pcm: int16 CUDA tensor with all pairs back to back; pcm_off: [B+1] sample offsets (host).
+        out: optional dict of preallocated CUDA tensors best_score f64[B], best_offset i32[B],
+        best_k i32[B].  Returns that dict; nothing is synchronised."""
+        import torch
+        B = len(pcm_off) - 1
+        K = len(self.ratios)
+        dev = pcm.device
+        if out is None:
+            out = {"best_score": torch.empty(B, dtype=torch.float64, device=dev),
+                   "best_offset": torch.empty(B, dtype=torch.int32, device=dev),
+                   "best_k": torch.empty(B, dtype=torch.int32, device=dev)}
+        a_s = all_out["score"].data_ptr() if all_out else None
+        a_o = all_out["offset"].data_ptr() if all_out else None
+        self.handle.sync_batch(
+            pcm.data_ptr(), pcm_off, self.frame_rate, self.sample_rate, self.non_speech_label,
+            self.energy_threshold, self.z_lo, self.z_hi, cue_start, cue_end, cue_keep, cue_off, self.ratios,
+            self.start_seconds, self.max_offset_samples, out["best_score"].data_ptr(),
+            out["best_offset"].data_ptr(), out["best_k"].data_ptr(), a_s, a_o, memspace=_native.B2_DEVICE)
+        assert K == len(self.ratios)
+        return out
+
+    def sync_host(self, pcm, pcm_off, cue_start, cue_end, cue_off, cue_keep=None, want_all=False):
+        """pcm: int16 numpy array (ideally backed by pinned memory).  Blocks until results are on
+        the host.  Returns (best_score, best_offset, best_k[, all_score, all_offset])."""
+        res = self.handle.sync_batch(
+            pcm, pcm_off, self.frame_rate, self.sample_rate, self.non_speech_label, self.energy_threshold,
+            self.z_lo, self.z_hi, cue_start, cue_end, cue_keep, cue_off, self.ratios, self.start_seconds,
+            self.max_offset_samples, want_all=want_all, memspace=_native.B2_HOST)
+        return res if want_all else res[:3]

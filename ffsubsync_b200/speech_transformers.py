@@ -287,7 +287,7 @@ class SubtitleSpeechTransformer(TransformerMixin, ComputeSpeechFrameBoundariesMi
             starts, ends, keep, [0, n], [1.0], 1, False, self.sample_rate, float(self.start_seconds),
             levels=[level])
         self.subtitle_speech_results_ = out.astype(np.float64)
-        if level != np.float32(level):  # keep the float64 level the reference writes
+        if level != 0.0:  # the kernel writes float32; restore the float64 level the reference writes
             self.subtitle_speech_results_[out != 0] = level
         self.fit_boundaries(self.subtitle_speech_results_)
         return self

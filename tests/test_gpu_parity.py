@@ -380,7 +380,16 @@ def test_sync_two_hour_pair_recovers_offset(handle):
     bs, bo, bk, a_s, a_o = handle.sync_batch(pcm, [0, len(pcm)], 16000, 100, 0.0, 100000, -1, -1, st, en,
                                              None, [0, len(st)], grid, 0.0, 6000, want_all=True)
     assert (bk[0], bo[0]) == (0, -2718)
-    ref_sig = (cls == 1).astype(float)
+    # reference-side signal from the numpy restatement of the detector, in 100 s chunks like the
+    # reference's loop (a few loud-hiss windows legitimately fall inside the zero-crossing band)
+    chunk = 1600000
+    ref_sig = np.concatenate([vo.energy_zcr_detect(pcm[i:i + chunk], 100, 16000, 0.0)
+                              for i in range(0, len(pcm), chunk)])
+    assert len(ref_sig) == 720000 and abs(int(ref_sig.sum()) - int((cls == 1).sum())) < 200
     sub = ro.rasterize(st, en, None, 100, 0, 1.0)[0]
-    assert bs[0] == ao.exact_score(ref_sig, sub, -2718)
+    assert bs[0] == ao.exact_score(ref_sig, sub, -2718)   # binary signals: exact integer
     assert np.all(a_s[1:] < bs[0])
+    subs = [ro.rasterize(st, en, None, 100, 0, r)[0] for r in grid]
+    for k in range(1, len(grid)):      # every ratio candidate: offset exact, score exact for +-1 x {-1, a}
+        ws, wo = ao.fft_align(ref_sig, subs[k], 6000)
+        assert a_o[k] == wo and _score_ok(a_s[k], ws)
