@@ -28,6 +28,7 @@ namespace {
 using namespace corr;
 
 constexpr int kCandMax = 32;
+constexpr int kRescoreSeg = 16;
 // candidates within kTauRel * sqrt(Es*Er) of the fp32 maximum are re-scored exactly; measured
 // round-off of the chain is < 6 * 2^-24 * sqrt(Es*Er) (tests/test_corr_emul.py, tests/test_gpu_align.py)
 constexpr float kTauRel = 64.0f * 5.9604645e-8f;
@@ -149,7 +150,7 @@ __global__ void __launch_bounds__(kThreads, 1)
 __global__ void __launch_bounds__(256) select_candidates_kernel(
     const SelJob* __restrict__ jobs, const float* __restrict__ scores,
     const float2* __restrict__ job_energy, int* __restrict__ cand_off,
-    int* __restrict__ cand_cnt) {
+    int* __restrict__ cand_cnt, int* __restrict__ work_list, int* __restrict__ work_count) {
   const SelJob job = jobs[blockIdx.x];
   const int tid = threadIdx.x;
   __shared__ float smax[256];
@@ -197,45 +198,61 @@ __global__ void __launch_bounds__(256) select_candidates_kernel(
     }
     __syncthreads();
   }
-  if (tid == 0) cand_cnt[blockIdx.x] = scount;
+  if (tid == 0) {
+    cand_cnt[blockIdx.x] = scount;
+    scount = min(scount, kCandMax);
+    swarp[0] = atomicAdd(work_count, scount);  // slots in the global re-score work list
+  }
+  __syncthreads();
+  if (tid < scount) work_list[swarp[0] + tid] = ((int)blockIdx.x << 5) | tid;
 }
 
 // ---- exact re-score ----------------------------------------------------------------------------
-// score(o) = sum over the overlap of (2 s[j] - 1)(2 r[j+o] - 1), float64, fixed summation order.
+// score(o) = sum over the overlap of (2 s[j] - 1)(2 r[j+o] - 1) in float64.  Each candidate's
+// overlap is cut into kRescoreSeg segments handled by different CTAs (persistent grid over the
+// work list); every partial sum has a fixed summation order and pick_kernel adds the partials in
+// segment order, so the result is deterministic.
 __global__ void __launch_bounds__(256) rescore_kernel(const SelJob* __restrict__ jobs,
                                                        const float* __restrict__ ref,
                                                        const float* __restrict__ sub,
                                                        const int* __restrict__ cand_off,
-                                                       const int* __restrict__ cand_cnt,
-                                                       double* __restrict__ cand_score) {
-  const int j = blockIdx.y, ci = blockIdx.x;
-  const int n = min(cand_cnt[j], kCandMax);
-  if (ci >= n) return;
-  const SelJob job = jobs[j];
-  const int o = cand_off[(size_t)j * kCandMax + ci];
-  const float* r = ref + job.ref_off;
-  const float* s = sub + job.sub_off;
-  const int j_lo = max(0, -o), j_hi = min(job.S, job.R - o);
-  double acc = 0.0;
-  for (int i = j_lo + threadIdx.x; i < j_hi; i += 256) {
-    const double a = 2.0 * (double)__ldg(s + i) - 1.0;
-    const double b = 2.0 * (double)__ldg(r + i + o) - 1.0;
-    acc = fma(a, b, acc);
-  }
+                                                       const int* __restrict__ work_list,
+                                                       const int* __restrict__ work_count,
+                                                       double* __restrict__ cand_partial) {
   __shared__ double sh[256];
-  sh[threadIdx.x] = acc;
-  __syncthreads();
-  for (int w = 128; w > 0; w >>= 1) {
-    if (threadIdx.x < w) sh[threadIdx.x] += sh[threadIdx.x + w];
+  const int total = *work_count * kRescoreSeg;
+  for (int w = blockIdx.x; w < total; w += gridDim.x) {
+    const int item = work_list[w / kRescoreSeg], seg = w % kRescoreSeg;
+    const int j = item >> 5, ci = item & 31;
+    const SelJob job = jobs[j];
+    const int o = cand_off[(size_t)j * kCandMax + ci];
+    const float* r = ref + job.ref_off;
+    const float* s = sub + job.sub_off;
+    const int j_lo = max(0, -o), j_hi = min(job.S, job.R - o);
+    const int len = max(0, j_hi - j_lo);
+    const int per = (len + kRescoreSeg - 1) / kRescoreSeg;
+    const int a0 = j_lo + seg * per, a1 = min(j_hi, a0 + per);
+    double acc = 0.0;
+    for (int i = a0 + threadIdx.x; i < a1; i += 256) {
+      const double a = 2.0 * (double)__ldg(s + i) - 1.0;
+      const double b = 2.0 * (double)__ldg(r + i + o) - 1.0;
+      acc = fma(a, b, acc);
+    }
+    sh[threadIdx.x] = acc;
+    __syncthreads();
+    for (int h = 128; h > 0; h >>= 1) {
+      if (threadIdx.x < h) sh[threadIdx.x] += sh[threadIdx.x + h];
+      __syncthreads();
+    }
+    if (threadIdx.x == 0) cand_partial[((size_t)j * kCandMax + ci) * kRescoreSeg + seg] = sh[0];
     __syncthreads();
   }
-  if (threadIdx.x == 0) cand_score[(size_t)j * kCandMax + ci] = sh[0];
 }
 
 __global__ void __launch_bounds__(128) pick_kernel(const SelJob* __restrict__ jobs, int n_jobs,
                                                     const int* __restrict__ cand_off,
                                                     const int* __restrict__ cand_cnt,
-                                                    const double* __restrict__ cand_score,
+                                                    const double* __restrict__ cand_partial,
                                                     double* __restrict__ score,
                                                     int32_t* __restrict__ offset,
                                                     int32_t* __restrict__ status) {
@@ -259,7 +276,8 @@ __global__ void __launch_bounds__(128) pick_kernel(const SelJob* __restrict__ jo
   double bs = -INFINITY;
   int bo = 0;
   for (int c = 0; c < n; ++c) {
-    const double s = cand_score[(size_t)j * kCandMax + c];
+    double s = 0.0;
+    for (int g = 0; g < kRescoreSeg; ++g) s += cand_partial[((size_t)j * kCandMax + c) * kRescoreSeg + g];
     const int o = cand_off[(size_t)j * kCandMax + c];
     if (c == 0 || s > bs || (s == bs && o > bo)) {
       bs = s;
@@ -373,10 +391,12 @@ int b2i_align_launch(b2_ctx* h, const float* d_ref, const int64_t* ref_off, cons
                 &d_scores));
   float* scores = (float*)d_scores;
   float2* job_energy = (float2*)((char*)d_scores + (((size_t)(score_total + 16) * 4 + 7) & ~size_t(7)));
-  B2_TRY(b2i_ws(h, b2_ctx::WS_CAND, J * kCandMax * 12 + J * 4 + 64, &d_cand));
-  double* cand_score = (double*)d_cand;
-  int* cand_off = (int*)(cand_score + J * kCandMax);
+  B2_TRY(b2i_ws(h, b2_ctx::WS_CAND, J * kCandMax * (8 * kRescoreSeg + 8) + J * 4 + 64, &d_cand));
+  double* cand_partial = (double*)d_cand;
+  int* cand_off = (int*)(cand_partial + J * kCandMax * kRescoreSeg);
   int* cand_cnt = cand_off + J * kCandMax;
+  int* work_list = cand_cnt + J;
+  int* work_count = work_list + J * kCandMax;
 
   B2_CUDA(h, cudaFuncSetAttribute(ref_spectra_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                   (int)kSmemBytes));
@@ -460,15 +480,16 @@ int b2i_align_launch(b2_ctx* h, const float* d_ref, const int64_t* ref_off, cons
   B2_TRY(b2i_meta_begin(h, &a, J * sizeof(SelJob) + 256));
   const SelJob* d_sel = (const SelJob*)b2i_meta_put(&a, sel.data(), J * sizeof(SelJob));
   B2_TRY(b2i_meta_commit(&a));
+  if (J >= (1u << 26)) B2_FAIL(h, B2_ERR_UNSUPPORTED, "align: B*K too large for one call");
+  B2_CUDA(h, cudaMemsetAsync(work_count, 0, sizeof(int), h->stream));
   select_candidates_kernel<<<(unsigned)J, 256, 0, h->stream>>>(d_sel, scores, job_energy, cand_off,
-                                                                cand_cnt);
+                                                                cand_cnt, work_list, work_count);
   B2_CHECK_LAUNCH(h, "select_candidates_kernel");
-  if (J > 65535) B2_FAIL(h, B2_ERR_UNSUPPORTED, "align: B*K > 65535 in one call");
-  rescore_kernel<<<dim3(kCandMax, (unsigned)J), 256, 0, h->stream>>>(d_sel, d_ref, d_sub, cand_off,
-                                                                      cand_cnt, cand_score);
+  rescore_kernel<<<(unsigned)(h->sm_count * 8), 256, 0, h->stream>>>(d_sel, d_ref, d_sub, cand_off,
+                                                                      work_list, work_count, cand_partial);
   B2_CHECK_LAUNCH(h, "rescore_kernel");
   pick_kernel<<<(unsigned)((J + 127) / 128), 128, 0, h->stream>>>(d_sel, (int)J, cand_off, cand_cnt,
-                                                                   cand_score, d_score, d_offset,
+                                                                   cand_partial, d_score, d_offset,
                                                                    d_status);
   B2_CHECK_LAUNCH(h, "pick_kernel");
   return B2_OK;

@@ -245,32 +245,66 @@ struct BlockSource {
   int t_lo, t_hi;
 };
 
-CORR_HD float2 load_pair(const BlockSource& s, int n, bool vec_ok) {
-  const int t = 2 * n;
-  float2 r = make_float2(0.f, 0.f);
-  if (vec_ok && t >= s.t_lo && t + 1 < s.t_hi) {
-    const float2 x = CORR_LDG(reinterpret_cast<const float2*>(s.src + t));
-    r.x = 2.f * x.x - 1.f;
-    r.y = 2.f * x.y - 1.f;
-  } else {
-    if (t >= s.t_lo && t < s.t_hi) r.x = 2.f * CORR_LDG(s.src + t) - 1.f;
-    if (t + 1 >= s.t_lo && t + 1 < s.t_hi) r.y = 2.f * CORR_LDG(s.src + t + 1) - 1.f;
+// The 16 complex inputs (32 samples) of one first-pass butterfly, j + q*1024, q = 0..15.
+// All global loads are issued back to back with clamped (always valid) addresses and masked
+// afterwards, so that the 16 (or 32) loads of a thread are in flight together; a branchy
+// per-element version serialised them on the memory latency (profiles/r1: 56 % long-scoreboard).
+CORR_HD void load_block16(const BlockSource& s, int j, float2 (&v)[16]) {
+  if (s.t_hi <= s.t_lo) {
+#pragma unroll
+    for (int q = 0; q < 16; ++q) v[q] = make_float2(0.f, 0.f);
+    return;
   }
-  return r;
+  const bool vec_ok = (reinterpret_cast<uintptr_t>(s.src) & 7) == 0;
+  const int n_lo = (s.t_lo + 1) >> 1, n_hi = s.t_hi >> 1;  // pairs fully inside [t_lo, t_hi)
+  if (vec_ok && n_hi > n_lo) {
+    const float2* src2 = reinterpret_cast<const float2*>(s.src);
+#pragma unroll
+    for (int q = 0; q < 16; ++q) {
+      const int n = j + (q << 10);
+      v[q] = CORR_LDG(src2 + min(max(n, n_lo), n_hi - 1));
+    }
+#pragma unroll
+    for (int q = 0; q < 16; ++q) {
+      const int n = j + (q << 10);
+      const bool full = (n >= n_lo) && (n < n_hi);
+      v[q].x = full ? 2.f * v[q].x - 1.f : 0.f;
+      v[q].y = full ? 2.f * v[q].y - 1.f : 0.f;
+    }
+    // at most two half-valid pairs per block (odd t_lo / odd t_hi)
+#pragma unroll
+    for (int q = 0; q < 16; ++q) {
+      const int n = j + (q << 10);
+      if ((s.t_lo & 1) && n == n_lo - 1) v[q].y = 2.f * CORR_LDG(s.src + s.t_lo) - 1.f;
+      if ((s.t_hi & 1) && n == n_hi) v[q].x = 2.f * CORR_LDG(s.src + s.t_hi - 1) - 1.f;
+    }
+  } else {
+    float a[16], b[16];
+#pragma unroll
+    for (int q = 0; q < 16; ++q) {
+      const int t0 = 2 * (j + (q << 10));
+      a[q] = CORR_LDG(s.src + min(max(t0, s.t_lo), s.t_hi - 1));
+      b[q] = CORR_LDG(s.src + min(max(t0 + 1, s.t_lo), s.t_hi - 1));
+    }
+#pragma unroll
+    for (int q = 0; q < 16; ++q) {
+      const int t0 = 2 * (j + (q << 10));
+      v[q].x = (t0 >= s.t_lo && t0 < s.t_hi) ? 2.f * a[q] - 1.f : 0.f;
+      v[q].y = (t0 + 1 >= s.t_lo && t0 + 1 < s.t_hi) ? 2.f * b[q] - 1.f : 0.f;
+    }
+  }
 }
 
 // First DIF pass (span 16384) reading the block straight from global memory.
 // Returns the thread's partial sum of squares of the (transformed) samples it loaded.
 CORR_HD float dif16_pass1_global(float2* buf, const Tables& t, int tid,
                                                     const BlockSource& s) {
-  const bool vec_ok = (reinterpret_cast<uintptr_t>(s.src) & 7) == 0;
   float ss = 0.f;
 #pragma unroll 1
   for (int rep = 0; rep < 2; ++rep) {
     const int j = tid + rep * kThreads;
     float2 v[16];
-#pragma unroll
-    for (int q = 0; q < 16; ++q) v[q] = load_pair(s, j + (q << 10), vec_ok);
+    load_block16(s, j, v);
 #pragma unroll
     for (int q = 0; q < 16; ++q) ss += v[q].x * v[q].x + v[q].y * v[q].y;
     bfly16_dif(v, pass_twiddle<10>(t, j));
@@ -396,12 +430,15 @@ CORR_HD void spec_store(const float2* buf, const Tables& t, int tid, float4* spe
 // Consumer: acc += conj(A) * B for the subtitle block spectrum in buf and the stored B.
 CORR_HD void sub_accumulate(SubState& st, const float2* buf, const Tables& t, int tid,
                             const float4* spec) {
+  // the stored reference spectrum is read one slot ahead of its use (global / L2 latency)
+  float4 b0 = CORR_LDG(spec + tid);
 #pragma unroll
   for (int u = 0; u < 16; ++u) {
     const int r = tid + u * kThreads;
+    const float4 b = b0;
+    if (u + 1 < 16) b0 = CORR_LDG(spec + r + kThreads);
     float2 hp, hq;
     untangle_slot(buf, t, r, hp, hq);
-    const float4 b = CORR_LDG(spec + r);
     float2 dp;
     if (u == 0 && tid == 0) {
       dp = make_float2(hp.x * b.x, hp.y * b.y);  // two real bins: DC and Nyquist

@@ -38,7 +38,7 @@ struct VadParams {
   long long total_tiles;
   long long pcm_total_bytes;
   long long e_min;            // fpw * energy_threshold
-  int B, fpw, G, tw, z_lo, z_hi, fast, stage_bytes;
+  int B, fpw, G, tw, z_lo, z_hi, fast, stage_bytes, cpl, stages;
   float label;
 };
 
@@ -92,9 +92,10 @@ __device__ __forceinline__ void accum_word(uint32_t w, uint32_t prev, long long&
 __global__ void __launch_bounds__(kThreads) vad_energy_zcr_kernel(VadParams p) {
   extern __shared__ __align__(128) unsigned char smem[];
   unsigned char* data = smem;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + (size_t)kStages * p.stage_bytes);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + (size_t)p.stages * p.stage_bytes);
   TileDesc* descs = reinterpret_cast<TileDesc*>(bars + kStages);
 
+  const int nst = p.stages;
   const int tid = threadIdx.x;
   if (tid == 0) {
     for (int s = 0; s < kStages; ++s) mbar_init(&bars[s], 1);
@@ -153,7 +154,7 @@ __global__ void __launch_bounds__(kThreads) vad_energy_zcr_kernel(VadParams p) {
 
   const long long first = blockIdx.x, stride = gridDim.x;
   if (tid == 0) {
-    for (int s = 0; s < kStages - 1; ++s) issue(first + (long long)s * stride, s);
+    for (int s = 0; s < nst - 1; ++s) issue(first + (long long)s * stride, s);
   }
 
   const int G = p.G;
@@ -162,9 +163,9 @@ __global__ void __launch_bounds__(kThreads) vad_energy_zcr_kernel(VadParams p) {
   const int fpw = p.fpw;
 
   for (long long it = 0;; ++it) {
-    const int stage = (int)(it % kStages);
-    const uint32_t parity = (uint32_t)((it / kStages) & 1);
-    if (tid == 0) issue(first + (it + kStages - 1) * stride, (int)((it + kStages - 1) % kStages));
+    const int stage = (int)(it % nst);
+    const uint32_t parity = (uint32_t)((it / nst) & 1);
+    if (tid == 0) issue(first + (it + nst - 1) * stride, (int)((it + nst - 1) % nst));
     mbar_wait(&bars[stage], parity);
     const TileDesc d = descs[stage];
     if (d.n_windows == 0) break;  // uniform: tiles are handed out in increasing order
@@ -182,15 +183,21 @@ __global__ void __launch_bounds__(kThreads) vad_energy_zcr_kernel(VadParams p) {
     const unsigned char* wbase = span + d.head_bytes + (size_t)wl * fpw * 2;
     if (full) {
       if (p.fast && d.head_bytes == 0) {
-        const int C = fpw >> 3;  // 16-byte chunks per window
-        for (int c = g; c < C; c += G) {
-          const uint4 v = *reinterpret_cast<const uint4*>(wbase + 16 * c);
-          const uint32_t pw =
-              c > 0 ? *reinterpret_cast<const uint32_t*>(wbase + 16 * c - 4) : (v.x << 16);
+        // lane g owns the contiguous 16-byte chunks [g*cpl, (g+1)*cpl) of its window (cpl odd =>
+        // LDS.128 conflict free); the sample before a chunk is carried in a register
+        const int cpl = p.cpl;
+        const unsigned char* cbase = wbase + 16 * g * cpl;
+        uint32_t pw = 0;
+        if (g > 0) pw = *reinterpret_cast<const uint32_t*>(cbase - 4);
+#pragma unroll 5
+        for (int c = 0; c < cpl; ++c) {
+          const uint4 v = *reinterpret_cast<const uint4*>(cbase + 16 * c);
+          if (c == 0 && g == 0) pw = v.x << 16;  // first sample of the window: no crossing
           accum_word(v.x, pw, e, z);
           accum_word(v.y, v.x, e, z);
           accum_word(v.z, v.y, e, z);
           accum_word(v.w, v.z, e, z);
+          pw = v.w;
         }
       } else {
         const short* xs = reinterpret_cast<const short*>(wbase);
@@ -262,18 +269,34 @@ int b2i_vad_launch(b2_ctx* h, const int16_t* d_pcm, const int64_t* pcm_off, int 
   if (((uintptr_t)d_pcm & 15) != 0)
     B2_FAIL(h, B2_ERR_BAD_ARG, "vad: device PCM pointer must be 16-byte aligned");
   VadParams p;
-  // lanes per window: keep >= 2 16-byte chunks per lane when possible
+  // lanes per window G: the vector path needs the window's C 16-byte chunks to split evenly over
+  // the lanes; prefer an odd chunks-per-lane count (conflict-free LDS.128) and tiles <= 64 KB
   const int C = fpw / 8;
-  int G = 4;
-  if (C > 32) G = 8;
-  if (C > 64) G = 16;
-  if (C > 128) G = 32;
+  p.fast = (fpw % 8 == 0) ? 1 : 0;
+  int G = 0, best_score = -1;
+  for (int g = 32; g >= 2 && p.fast; g >>= 1) {
+    if (C % g != 0) continue;
+    const int cpl = C / g;
+    const long long tile = (long long)(kThreads / g) * fpw * 2;
+    const int score = ((cpl & 1) ? 4 : 0) + (tile <= 65536 ? 2 : 0) + (cpl >= 3 ? 1 : 0);
+    if (score > best_score) { best_score = score; G = g; }
+  }
+  if (G == 0) {  // generic 16-bit path: any window size
+    p.fast = 0;
+    G = 4;
+    if (C > 32) G = 8;
+    if (C > 64) G = 16;
+    if (C > 128) G = 32;
+  }
   p.G = G;
+  p.cpl = p.fast ? C / G : 0;
   p.tw = kThreads / G;
   p.fpw = fpw;
-  p.fast = (fpw % 8 == 0) ? 1 : 0;
   p.stage_bytes = ((p.tw * fpw * 2 + 32) + 127) & ~127;
-  size_t smem = (size_t)kStages * p.stage_bytes + kStages * sizeof(uint64_t) +
+  int stages = kStages;
+  while (stages > 2 && (size_t)stages * p.stage_bytes > 200 * 1024) --stages;
+  p.stages = stages;
+  size_t smem = (size_t)stages * p.stage_bytes + kStages * sizeof(uint64_t) +
                 kStages * sizeof(TileDesc) + 64;
   if (smem > 227 * 1024) B2_FAIL(h, B2_ERR_UNSUPPORTED, "vad: window of %d samples too large", fpw);
 
