@@ -56,6 +56,11 @@ struct SelJob {        // one (pair, ratio)
   int masked_offset;   // offset reported when kind == 2
 };
 
+// Bulk L2 prefetch (16-byte aligned address, size a multiple of 16).
+__device__ __forceinline__ void l2_prefetch(const void* p, uint32_t bytes) {
+  asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(p), "r"(bytes) : "memory");
+}
+
 // ------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(kThreads, 1)
     ref_spectra_kernel(const float* __restrict__ ref, const SpecItem* __restrict__ items,
@@ -111,6 +116,15 @@ __global__ void __launch_bounds__(kThreads, 1)
   float er = 0.f;
   for (int blk = job.blk_lo; blk < job.blk_hi; ++blk) {
     const int j0 = blk * L;
+    if (tid == 0 && blk + 1 < job.blk_hi) {
+      // pull the next block's samples and reference spectrum into L2 while this block computes
+      const int jn = j0 + L;
+      const float* nsrc = sub + job.sub_off + jn;
+      const uintptr_t a0 = (reinterpret_cast<uintptr_t>(nsrc) + 15) & ~uintptr_t(15);
+      const uintptr_t a1 = reinterpret_cast<uintptr_t>(nsrc + min(job.S - jn, L)) & ~uintptr_t(15);
+      if (a1 > a0) l2_prefetch(reinterpret_cast<const void*>(a0), (uint32_t)(a1 - a0));
+      l2_prefetch(spec + (size_t)(job.spec_base + (blk + 1 - job.blk_lo)) * kPairs, kPairs * 16);
+    }
     BlockSource s;
     s.src = sub + job.sub_off + j0;
     s.t_lo = 0;

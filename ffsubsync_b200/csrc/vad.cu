@@ -9,24 +9,27 @@
 // window is non-speech.
 //
 // Roofline: pure HBM stream, 2*fpw bytes in -> 4 bytes out per window (320 B -> 4 B at 16 kHz).
-// Persistent CTAs; each tile of TW windows is moved HBM -> shared memory by one 1-D TMA bulk
-// copy (cp.async.bulk + mbarrier complete_tx, SASS UBLKCP) into a STAGES-deep ring so that
-// >= 60 KB per SM is in flight; consumers read the staged windows with conflict-free LDS.128.
+// Persistent, warp-specialised CTAs: one producer warp moves tiles of TW windows HBM -> shared
+// memory with 1-D TMA bulk copies (cp.async.bulk + mbarrier complete_tx, SASS UBLKCP) into a
+// ring of stages; eight consumer warps wait on the stage's "full" mbarrier, reduce their windows
+// straight out of shared memory (conflict-free LDS.128) and release the stage through its
+// "empty" mbarrier - no CTA-wide barrier on the steady-state path.
 #include "common.cuh"
 
 namespace {
 
-constexpr int kThreads = 256;
-constexpr int kStages = 4;
+constexpr int kConsumerThreads = 256;
+constexpr int kThreads = kConsumerThreads + 32;  // + one producer warp
+constexpr int kMaxStages = 4;
 
 struct TileDesc {
   long long out_base;   // index into out[] of the tile's first window
   long long n_left;     // samples of the signal from the tile's first sample to the signal end
+  long long span_gbyte; // global byte offset of the staged span start
   int n_windows;        // windows in this tile (0 = no more tiles for this CTA)
   int head_bytes;       // offset of the first sample inside the 16 B-aligned staged span
   int tail_src_off;     // >=0: bytes [tail_src_off, tail_end) of the span must be copied by hand
   int tail_end;
-  long long span_gbyte; // global byte address offset of the staged span start
 };
 
 struct VadParams {
@@ -79,101 +82,146 @@ __device__ __forceinline__ void tma_bulk_g2s(void* dst, const void* src, uint32_
       : "memory");
 }
 
-__device__ __forceinline__ void accum_word(uint32_t w, uint32_t prev, long long& e, int& z) {
-  int lo = (int)(short)(w & 0xffffu);
-  int hi = ((int)w) >> 16;
-  e += (long long)lo * lo;
-  e += (long long)hi * hi;
-  // f = [x_2k : x_2k-1]; (w ^ f) has the 2k-1 -> 2k sign change in bit 15, 2k -> 2k+1 in bit 31
-  uint32_t f = __funnelshift_l(prev, w, 16);
+// One 32-bit word = samples (x0 = low half, x1 = high half).
+//   energy: x^2 = x*lo8(x) + 256*x*hi8(x) (lo8 unsigned, hi8 signed) -> two 2-way 16x8 dot products
+//   crossings: f = [x0 : previous sample]; (w ^ f) carries prev->x0 in bit 15, x0->x1 in bit 31
+__device__ __forceinline__ void accum_word(uint32_t w, uint32_t prev, int& e_lo, int& e_hi, int& z) {
+  const uint32_t perm = __byte_perm(w, 0u, 0x3120);  // bytes [lo8(x0), lo8(x1), hi8(x0), hi8(x1)]
+  asm("dp2a.lo.s32.u32 %0, %1, %2, %0;" : "+r"(e_lo) : "r"(w), "r"(perm));
+  asm("dp2a.hi.s32.s32 %0, %1, %2, %0;" : "+r"(e_hi) : "r"(w), "r"(perm));
+  const uint32_t f = __funnelshift_l(prev, w, 16);
   z += __popc((w ^ f) & 0x80008000u);
+}
+
+// Lane g of a window owns the contiguous 16-byte chunks [g*CPL, (g+1)*CPL).
+template <int CPL>
+__device__ __forceinline__ void window_part_fast(const unsigned char* wbase, int g, int cpl_rt,
+                                                 long long& e, int& z) {
+  const int cpl = CPL > 0 ? CPL : cpl_rt;
+  const unsigned char* cbase = wbase + 16 * g * cpl;
+  uint32_t pw = 0;
+  if (g > 0) pw = *reinterpret_cast<const uint32_t*>(cbase - 4);
+  int e_lo = 0, e_hi = 0;
+  if (CPL > 0) {
+    uint4 v[CPL > 0 ? CPL : 1];
+#pragma unroll
+    for (int c = 0; c < CPL; ++c) v[c] = *reinterpret_cast<const uint4*>(cbase + 16 * c);
+    if (g == 0) pw = v[0].x << 16;  // first sample of the window: no crossing before it
+#pragma unroll
+    for (int c = 0; c < CPL; ++c) {
+      accum_word(v[c].x, pw, e_lo, e_hi, z);
+      accum_word(v[c].y, v[c].x, e_lo, e_hi, z);
+      accum_word(v[c].z, v[c].y, e_lo, e_hi, z);
+      accum_word(v[c].w, v[c].z, e_lo, e_hi, z);
+      pw = v[c].w;
+    }
+    e += (long long)e_lo + (long long)e_hi * 256LL;
+  } else {
+    for (int c = 0; c < cpl; ++c) {
+      const uint4 v = *reinterpret_cast<const uint4*>(cbase + 16 * c);
+      if (c == 0 && g == 0) pw = v.x << 16;
+      accum_word(v.x, pw, e_lo, e_hi, z);
+      accum_word(v.y, v.x, e_lo, e_hi, z);
+      accum_word(v.z, v.y, e_lo, e_hi, z);
+      accum_word(v.w, v.z, e_lo, e_hi, z);
+      pw = v.w;
+      if ((c & 15) == 15) {  // keep the 32-bit partial sums far from overflow
+        e += (long long)e_lo + (long long)e_hi * 256LL;
+        e_lo = e_hi = 0;
+      }
+    }
+    e += (long long)e_lo + (long long)e_hi * 256LL;
+  }
 }
 
 __global__ void __launch_bounds__(kThreads) vad_energy_zcr_kernel(VadParams p) {
   extern __shared__ __align__(128) unsigned char smem[];
   unsigned char* data = smem;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + (size_t)p.stages * p.stage_bytes);
-  TileDesc* descs = reinterpret_cast<TileDesc*>(bars + kStages);
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + (size_t)p.stages * p.stage_bytes);
+  uint64_t* empty_bar = full_bar + kMaxStages;
+  TileDesc* descs = reinterpret_cast<TileDesc*>(empty_bar + kMaxStages);
 
   const int nst = p.stages;
   const int tid = threadIdx.x;
   if (tid == 0) {
-    for (int s = 0; s < kStages; ++s) mbar_init(&bars[s], 1);
+    for (int s = 0; s < kMaxStages; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], kConsumerThreads / 32);
+    }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   __syncthreads();
-
-  // ---- producer state (thread 0 only) ----
-  int cur_b = 0;
-  auto issue = [&](long long t, int stage) {
-    TileDesc d;
-    if (t >= p.total_tiles) {
-      d.n_windows = 0;
-      d.out_base = d.n_left = d.span_gbyte = 0;
-      d.head_bytes = 0;
-      d.tail_src_off = -1;
-      d.tail_end = 0;
-      descs[stage] = d;
-      mbar_arrive(&bars[stage]);
-      return;
-    }
-    while (t >= p.tile_off[cur_b + 1]) ++cur_b;
-    const long long w0 = (t - p.tile_off[cur_b]) * p.tw;
-    const long long sig0 = p.pcm_off[cur_b], sig1 = p.pcm_off[cur_b + 1];
-    const long long n = sig1 - sig0;
-    const long long nwin = (n + p.fpw - 1) / p.fpw;
-    const int nw = (int)min((long long)p.tw, nwin - w0);
-    const long long s0 = sig0 + w0 * p.fpw;
-    const long long s1 = min(s0 + (long long)nw * p.fpw, sig1);
-    const long long b0 = 2 * s0, b1 = 2 * s1;
-    const long long a0 = b0 & ~15LL;
-    const long long a1 = (b1 + 15) & ~15LL;
-    const long long limit = p.pcm_total_bytes & ~15LL;  // bulk copies stay inside the buffer
-    const long long bulk_end = min(a1, limit);
-    const uint32_t bulk = bulk_end > a0 ? (uint32_t)(bulk_end - a0) : 0u;
-    d.n_windows = nw;
-    d.out_base = p.out_off[cur_b] + w0;
-    d.n_left = sig1 - s0;
-    d.head_bytes = (int)(b0 - a0);
-    d.span_gbyte = a0;
-    if (bulk_end < b1) {  // ragged end of the whole buffer: < 16 bytes copied by hand
-      d.tail_src_off = (int)(max(bulk_end, a0) - a0);
-      d.tail_end = (int)(b1 - a0);
-    } else {
-      d.tail_src_off = -1;
-      d.tail_end = 0;
-    }
-    descs[stage] = d;
-    if (bulk) {
-      mbar_arrive_expect_tx(&bars[stage], bulk);
-      tma_bulk_g2s(data + (size_t)stage * p.stage_bytes, p.pcm_bytes + a0, bulk, &bars[stage]);
-    } else {
-      mbar_arrive(&bars[stage]);
-    }
-  };
-
   const long long first = blockIdx.x, stride = gridDim.x;
-  if (tid == 0) {
-    for (int s = 0; s < nst - 1; ++s) issue(first + (long long)s * stride, s);
+
+  if (tid >= kConsumerThreads) {
+    // ================================ producer warp ==========================================
+    if (tid != kConsumerThreads) return;
+    int cur_b = 0;
+    for (long long it = 0;; ++it) {
+      const int stage = (int)(it % nst);
+      if (it >= nst) mbar_wait(&empty_bar[stage], (uint32_t)(((it / nst) - 1) & 1));
+      const long long t = first + it * stride;
+      TileDesc d;
+      if (t >= p.total_tiles) {
+        d.n_windows = 0;
+        d.out_base = d.n_left = d.span_gbyte = 0;
+        d.head_bytes = 0;
+        d.tail_src_off = -1;
+        d.tail_end = 0;
+        descs[stage] = d;
+        mbar_arrive(&full_bar[stage]);
+        return;
+      }
+      while (t >= p.tile_off[cur_b + 1]) ++cur_b;
+      const long long w0 = (t - p.tile_off[cur_b]) * p.tw;
+      const long long sig0 = p.pcm_off[cur_b], sig1 = p.pcm_off[cur_b + 1];
+      const long long nwin = p.out_off[cur_b + 1] - p.out_off[cur_b];
+      const int nw = (int)min((long long)p.tw, nwin - w0);
+      const long long s0 = sig0 + w0 * p.fpw;
+      const long long s1 = min(s0 + (long long)nw * p.fpw, sig1);
+      const long long b0 = 2 * s0, b1 = 2 * s1;
+      const long long a0 = b0 & ~15LL;
+      const long long a1 = (b1 + 15) & ~15LL;
+      const long long limit = p.pcm_total_bytes & ~15LL;  // bulk copies stay inside the buffer
+      const long long bulk_end = min(a1, limit);
+      const uint32_t bulk = bulk_end > a0 ? (uint32_t)(bulk_end - a0) : 0u;
+      d.n_windows = nw;
+      d.out_base = p.out_off[cur_b] + w0;
+      d.n_left = sig1 - s0;
+      d.head_bytes = (int)(b0 - a0);
+      d.span_gbyte = a0;
+      if (bulk_end < b1) {  // ragged end of the whole buffer: < 16 bytes copied by hand
+        d.tail_src_off = (int)(max(bulk_end, a0) - a0);
+        d.tail_end = (int)(b1 - a0);
+      } else {
+        d.tail_src_off = -1;
+        d.tail_end = 0;
+      }
+      descs[stage] = d;
+      if (bulk) {
+        mbar_arrive_expect_tx(&full_bar[stage], bulk);
+        tma_bulk_g2s(data + (size_t)stage * p.stage_bytes, p.pcm_bytes + a0, bulk, &full_bar[stage]);
+      } else {
+        mbar_arrive(&full_bar[stage]);
+      }
+    }
   }
 
+  // ================================== consumer warps ==========================================
   const int G = p.G;
   const int g = tid % G;
   const int wl = tid / G;
   const int fpw = p.fpw;
-
   for (long long it = 0;; ++it) {
     const int stage = (int)(it % nst);
-    const uint32_t parity = (uint32_t)((it / nst) & 1);
-    if (tid == 0) issue(first + (it + nst - 1) * stride, (int)((it + nst - 1) % nst));
-    mbar_wait(&bars[stage], parity);
+    mbar_wait(&full_bar[stage], (uint32_t)((it / nst) & 1));
     const TileDesc d = descs[stage];
-    if (d.n_windows == 0) break;  // uniform: tiles are handed out in increasing order
+    if (d.n_windows == 0) break;
     unsigned char* span = data + (size_t)stage * p.stage_bytes;
     if (d.tail_src_off >= 0) {  // rare: last < 16 bytes of the whole PCM buffer
       const int nb = d.tail_end - d.tail_src_off;
       if (tid < nb) span[d.tail_src_off + tid] = p.pcm_bytes[d.span_gbyte + d.tail_src_off + tid];
-      __syncthreads();
+      asm volatile("bar.sync 1, %0;" ::"n"(kConsumerThreads) : "memory");
     }
     long long e = 0;
     int z = 0;
@@ -183,22 +231,9 @@ __global__ void __launch_bounds__(kThreads) vad_energy_zcr_kernel(VadParams p) {
     const unsigned char* wbase = span + d.head_bytes + (size_t)wl * fpw * 2;
     if (full) {
       if (p.fast && d.head_bytes == 0) {
-        // lane g owns the contiguous 16-byte chunks [g*cpl, (g+1)*cpl) of its window (cpl odd =>
-        // LDS.128 conflict free); the sample before a chunk is carried in a register
-        const int cpl = p.cpl;
-        const unsigned char* cbase = wbase + 16 * g * cpl;
-        uint32_t pw = 0;
-        if (g > 0) pw = *reinterpret_cast<const uint32_t*>(cbase - 4);
-#pragma unroll 5
-        for (int c = 0; c < cpl; ++c) {
-          const uint4 v = *reinterpret_cast<const uint4*>(cbase + 16 * c);
-          if (c == 0 && g == 0) pw = v.x << 16;  // first sample of the window: no crossing
-          accum_word(v.x, pw, e, z);
-          accum_word(v.y, v.x, e, z);
-          accum_word(v.z, v.y, e, z);
-          accum_word(v.w, v.z, e, z);
-          pw = v.w;
-        }
+        if (p.cpl == 5) window_part_fast<5>(wbase, g, 5, e, z);          // 16 kHz, 4 lanes/window
+        else if (p.cpl == 15) window_part_fast<15>(wbase, g, 15, e, z);  // 48 kHz, 4 lanes/window
+        else window_part_fast<0>(wbase, g, p.cpl, e, z);
       } else {
         const short* xs = reinterpret_cast<const short*>(wbase);
         for (int i = g; i < fpw; i += G) {
@@ -217,7 +252,8 @@ __global__ void __launch_bounds__(kThreads) vad_energy_zcr_kernel(VadParams p) {
       const bool speech = full && e >= p.e_min && z >= p.z_lo && z <= p.z_hi;
       p.out[d.out_base + wl] = speech ? 1.0f : p.label;
     }
-    __syncthreads();  // stage fully consumed -> may be refilled by the next issue
+    __syncwarp();
+    if ((tid & 31) == 0) mbar_arrive(&empty_bar[stage]);  // this warp is done with the stage
   }
 }
 
@@ -277,7 +313,7 @@ int b2i_vad_launch(b2_ctx* h, const int16_t* d_pcm, const int64_t* pcm_off, int 
   for (int g = 32; g >= 2 && p.fast; g >>= 1) {
     if (C % g != 0) continue;
     const int cpl = C / g;
-    const long long tile = (long long)(kThreads / g) * fpw * 2;
+    const long long tile = (long long)(kConsumerThreads / g) * fpw * 2;
     const int score = ((cpl & 1) ? 4 : 0) + (tile <= 65536 ? 2 : 0) + (cpl >= 3 ? 1 : 0);
     if (score > best_score) { best_score = score; G = g; }
   }
@@ -290,14 +326,14 @@ int b2i_vad_launch(b2_ctx* h, const int16_t* d_pcm, const int64_t* pcm_off, int 
   }
   p.G = G;
   p.cpl = p.fast ? C / G : 0;
-  p.tw = kThreads / G;
+  p.tw = kConsumerThreads / G;
   p.fpw = fpw;
   p.stage_bytes = ((p.tw * fpw * 2 + 32) + 127) & ~127;
-  int stages = kStages;
+  int stages = kMaxStages;
   while (stages > 2 && (size_t)stages * p.stage_bytes > 200 * 1024) --stages;
   p.stages = stages;
-  size_t smem = (size_t)stages * p.stage_bytes + kStages * sizeof(uint64_t) +
-                kStages * sizeof(TileDesc) + 64;
+  size_t smem = (size_t)stages * p.stage_bytes + 2 * kMaxStages * sizeof(uint64_t) +
+                kMaxStages * sizeof(TileDesc) + 64;
   if (smem > 227 * 1024) B2_FAIL(h, B2_ERR_UNSUPPORTED, "vad: window of %d samples too large", fpw);
 
   std::vector<long long> tile_off(B + 1);
