@@ -314,7 +314,7 @@ def cpu_baseline_sample(K, ratios, budget_pairs=None):
     for v in ("OMP_NUM_THREADS", "MKL_NUM_THREADS", "OPENBLAS_NUM_THREADS"):
         os.environ[v] = "1"
     cores = os.cpu_count() or 1
-    used = max(1, min(cores, 32))
+    used = max(1, min(cores, 128))
     _cpu_setup(ratios)
     n_pairs = budget_pairs or used
     rate, dt = cpu_pass(n_pairs, used)
@@ -333,7 +333,7 @@ def run_reference(args):
     for v in ("OMP_NUM_THREADS", "MKL_NUM_THREADS", "OPENBLAS_NUM_THREADS"):
         os.environ[v] = "1"
     cores = os.cpu_count() or 1
-    used = max(1, min(cores, 32))
+    used = max(1, min(cores, 128))
     _cpu_setup(ratios)
     per_step = used
     for _ in range(min(args.warmup, 1)):   # one warm-up pass is enough for a CPU pool; bounded runtime
@@ -366,8 +366,9 @@ def main():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--pairs", type=int, default=int(os.environ.get("B2_BENCH_PAIRS", "64")),
-                    help="2 h pairs per GPU per step")
+    ap.add_argument("--pairs", type=int, default=int(os.environ.get("B2_BENCH_PAIRS", "148")),
+                    help="2 h pairs per GPU per step (default: one per SM, so that pairs x ratios "
+                         "correlation jobs fill whole waves of 148 CTAs; 34 GB of PCM per GPU)")
     ap.add_argument("--ratios", type=int, default=5)
     ap.add_argument("--e2e-pairs", type=int, default=4)
     ap.add_argument("--no-cpu-baseline", action="store_true")

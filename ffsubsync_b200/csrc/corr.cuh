@@ -40,8 +40,23 @@ CORR_HD float2 cmul(float2 a, float2 b) {
 CORR_HD float2 cmul_conj_a(float2 a, float2 b) {  // conj(a) * b
   return make_float2(a.x * b.x + a.y * b.y, a.x * b.y - a.y * b.x);
 }
-CORR_HD float2 cadd(float2 a, float2 b) { return make_float2(a.x + b.x, a.y + b.y); }
-CORR_HD float2 csub(float2 a, float2 b) { return make_float2(a.x - b.x, a.y - b.y); }
+// Blackwell packed fp32x2 arithmetic (SASS FADD2 / FFMA2): one instruction per complex add.
+CORR_HD float2 padd(float2 a, float2 b) {
+#if defined(__CUDA_ARCH__) && __CUDA_ARCH__ >= 1000
+  return __fadd2_rn(a, b);
+#else
+  return make_float2(a.x + b.x, a.y + b.y);
+#endif
+}
+CORR_HD float2 pfma(float2 a, float2 b, float2 c) {  // a*b + c, componentwise
+#if defined(__CUDA_ARCH__) && __CUDA_ARCH__ >= 1000
+  return __ffma2_rn(a, b, c);
+#else
+  return make_float2(a.x * b.x + c.x, a.y * b.y + c.y);
+#endif
+}
+CORR_HD float2 cadd(float2 a, float2 b) { return padd(a, b); }
+CORR_HD float2 csub(float2 a, float2 b) { return pfma(b, make_float2(-1.f, -1.f), a); }
 CORR_HD float2 cconj(float2 a) { return make_float2(a.x, -a.y); }
 
 // position <-> frequency of the in-place DIF output, radices (16,16,16,4)
@@ -84,12 +99,15 @@ CORR_HD void r4(float2& a0, float2& a1, float2& a2, float2& a3) {
   const float2 t0 = cadd(a0, a2), t1 = csub(a0, a2), t2 = cadd(a1, a3), t3 = csub(a1, a3);
   a0 = cadd(t0, t2);
   a2 = csub(t0, t2);
+  // -/+ i * t3 = (+-t3.y, -+t3.x): one swapped copy feeds both outputs
+  const float2 sw = make_float2(t3.y, t3.x);
+  const float2 pm = make_float2(1.f, -1.f), mp = make_float2(-1.f, 1.f);
   if (!INV) {
-    a1 = make_float2(t1.x + t3.y, t1.y - t3.x);
-    a3 = make_float2(t1.x - t3.y, t1.y + t3.x);
+    a1 = pfma(sw, pm, t1);
+    a3 = pfma(sw, mp, t1);
   } else {
-    a1 = make_float2(t1.x - t3.y, t1.y + t3.x);
-    a3 = make_float2(t1.x + t3.y, t1.y - t3.x);
+    a1 = pfma(sw, mp, t1);
+    a3 = pfma(sw, pm, t1);
   }
 }
 
@@ -430,13 +448,15 @@ CORR_HD void spec_store(const float2* buf, const Tables& t, int tid, float4* spe
 // Consumer: acc += conj(A) * B for the subtitle block spectrum in buf and the stored B.
 CORR_HD void sub_accumulate(SubState& st, const float2* buf, const Tables& t, int tid,
                             const float4* spec) {
-  // the stored reference spectrum is read one slot ahead of its use (global / L2 latency)
+  // the stored reference spectrum is read two slots ahead of its use (L2 latency)
   float4 b0 = CORR_LDG(spec + tid);
+  float4 b1 = CORR_LDG(spec + tid + kThreads);
 #pragma unroll
   for (int u = 0; u < 16; ++u) {
     const int r = tid + u * kThreads;
     const float4 b = b0;
-    if (u + 1 < 16) b0 = CORR_LDG(spec + r + kThreads);
+    b0 = b1;
+    if (u + 2 < 16) b1 = CORR_LDG(spec + r + 2 * kThreads);
     float2 hp, hq;
     untangle_slot(buf, t, r, hp, hq);
     float2 dp;
