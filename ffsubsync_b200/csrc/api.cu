@@ -55,6 +55,11 @@ extern "C" int b2_destroy(b2_handle h) {
     if (w.p) cudaFree(w.p);
   for (auto& p : h->pinned)
     if (p.p) cudaFreeHost(p.p);
+  for (auto& m : h->meta) {
+    if (m.d) cudaFree(m.d);
+    if (m.p) cudaFreeHost(m.p);
+    if (m.ev) cudaEventDestroy(m.ev);
+  }
   if (h->own_stream && h->stream) cudaStreamDestroy(h->stream);
   delete h;
   return B2_OK;
@@ -125,18 +130,35 @@ int b2i_pinned(b2_ctx* h, int which, size_t bytes, void** out) {
 
 // Metadata arena: host-side tables (offsets, per-job parameters) are packed into one pinned
 // block and uploaded with a single async copy per call.
+// Arenas come from a ring of kMetaSlots (pinned, device) buffer pairs so that the host can plan
+// and upload several launches ahead of the GPU without synchronising the stream.  A slot is
+// reused kMetaSlots arenas later; the event recorded at the commit of the arena that FOLLOWED its
+// previous use guarantees (in-order stream) that both its upload and every kernel that read its
+// device copy have finished.
 int b2i_meta_begin(b2_ctx* h, MetaArena* a, size_t bytes) {
   a->h = h;
   bytes = (bytes + 255) & ~size_t(255);
-  // The pinned block may still be the source of the previous call's async copy.
-  B2_CUDA(h, cudaStreamSynchronize(h->stream));
-  void *d, *p;
-  B2_TRY(b2i_ws(h, b2_ctx::WS_META, bytes, &d));
-  B2_TRY(b2i_pinned(h, 0, bytes, &p));
-  a->dbase = (char*)d;
-  a->hbase = (char*)p;
+  const int slot = (int)(h->meta_seq % b2_ctx::kMetaSlots);
+  b2_ctx::MetaSlot& next = h->meta[(slot + 1) % b2_ctx::kMetaSlots];
+  if (h->meta_seq >= (uint64_t)b2_ctx::kMetaSlots && next.ev) B2_CUDA(h, cudaEventSynchronize(next.ev));
+  b2_ctx::MetaSlot& s = h->meta[slot];
+  if (!s.ev) B2_CUDA(h, cudaEventCreateWithFlags(&s.ev, cudaEventDisableTiming));
+  if (bytes > s.cap) {
+    if (s.d) B2_CUDA(h, cudaFree(s.d));
+    if (s.p) B2_CUDA(h, cudaFreeHost(s.p));
+    s.d = s.p = nullptr;
+    s.cap = 0;
+    const size_t want = bytes + bytes / 4 + 4096;
+    B2_CUDA(h, cudaMalloc(&s.d, want));
+    B2_CUDA(h, cudaMallocHost(&s.p, want));
+    s.cap = want;
+  }
+  a->slot = slot;
+  a->dbase = (char*)s.d;
+  a->hbase = (char*)s.p;
   a->cap = bytes;
   a->used = 0;
+  h->meta_seq++;
   return B2_OK;
 }
 
@@ -159,6 +181,7 @@ int b2i_meta_commit(MetaArena* a) {
   b2_ctx* h = a->h;
   if (a->used)
     B2_CUDA(h, cudaMemcpyAsync(a->dbase, a->hbase, a->used, cudaMemcpyHostToDevice, h->stream));
+  B2_CUDA(h, cudaEventRecord(h->meta[a->slot].ev, h->stream));
   return B2_OK;
 }
 
@@ -375,7 +398,7 @@ extern "C" int b2_align_batch(b2_handle h, const float* ref, const int64_t* ref_
     d_status = d_offset + J;
   }
   B2_TRY(b2i_align_launch(h, d_ref, ref_off, d_sub, sub_off, B, K, max_offset_samples, d_score,
-                          d_offset, d_status));
+                          d_offset, d_status, /*winner_only=*/0));
   if (memspace == B2_HOST) {
     B2_TRY(copy_out(h, score, d_score, J * 8));
     B2_TRY(copy_out(h, offset, d_offset, J * 4));
@@ -483,8 +506,12 @@ extern "C" int b2_sync_batch(b2_handle h, const int16_t* pcm, const int64_t* pcm
                            sample_rate, start_seconds, (float*)d_subsig, sub_off.data()));
   double* o_score = (memspace == B2_DEVICE && all_score) ? all_score : d_score;
   int32_t* o_offset = (memspace == B2_DEVICE && all_offset) ? all_offset : d_offset;
+  // only the best ratio of each pair is reported unless the per-ratio arrays are requested:
+  // ratios that provably cannot win are then not re-scored exactly (B2_ALIGN_APPROX)
+  const int winner_only = (!all_score && !all_offset) ? 1 : 0;
   B2_TRY(b2i_align_launch(h, (const float*)d_refsig, ref_off.data(), (const float*)d_subsig,
-                          sub_off.data(), B, K, max_offset_samples, o_score, o_offset, d_status));
+                          sub_off.data(), B, K, max_offset_samples, o_score, o_offset, d_status,
+                          winner_only));
   if (memspace == B2_DEVICE) {
     B2_TRY(b2i_reduce_launch(h, o_score, o_offset, d_status, B, K, max_offset_samples, best_score,
                              best_offset, best_k));

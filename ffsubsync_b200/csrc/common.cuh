@@ -35,6 +35,16 @@ struct b2_ctx {
          WS_SIG_REF, WS_SIG_SUB, WS_MISC, WS_COUNT };
   DeviceBuf ws[WS_COUNT];
   HostBuf pinned[4];
+  // ring of metadata upload buffers (see b2i_meta_begin)
+  static const int kMetaSlots = 8;
+  struct MetaSlot {
+    void* d = nullptr;
+    void* p = nullptr;
+    size_t cap = 0;
+    cudaEvent_t ev = nullptr;
+  };
+  MetaSlot meta[kMetaSlots];
+  uint64_t meta_seq = 0;
 };
 
 #define B2_FAIL(h, code, ...)                          \
@@ -75,6 +85,7 @@ struct MetaArena {
   char* dbase = nullptr;
   char* hbase = nullptr;
   size_t cap = 0, used = 0;
+  int slot = 0;
 };
 int b2i_meta_begin(b2_ctx* h, MetaArena* a, size_t bytes);
 void* b2i_meta_put(MetaArena* a, const void* src, size_t bytes);  // returns device pointer
@@ -98,7 +109,7 @@ int b2i_bounds_launch(b2_ctx* h, const float* d_sig, const int64_t* off_host, in
 int b2i_align_launch(b2_ctx* h, const float* d_ref, const int64_t* ref_off_host,
                      const float* d_sub, const int64_t* sub_off_host, int B, int K,
                      int32_t max_offset_samples, double* d_score, int32_t* d_offset,
-                     int32_t* d_status);
+                     int32_t* d_status, int winner_only);
 int b2i_reduce_launch(b2_ctx* h, const double* d_score, const int32_t* d_offset,
                       const int32_t* d_status, int B, int K, int32_t max_offset_samples,
                       double* d_best_score, int32_t* d_best_offset, int32_t* d_best_k);

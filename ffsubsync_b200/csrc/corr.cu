@@ -161,17 +161,16 @@ __global__ void __launch_bounds__(kThreads, 1)
 // Per (pair, ratio): approximate maximum over the surviving window, then every offset whose
 // fp32 score is within tau of it, taken from the LARGEST offset down (np.argmax returns the
 // lowest index = largest offset among equal values), at most kCandMax of them.
-__global__ void __launch_bounds__(256) select_candidates_kernel(
-    const SelJob* __restrict__ jobs, const float* __restrict__ scores,
-    const float2* __restrict__ job_energy, int* __restrict__ cand_off,
-    int* __restrict__ cand_cnt, int* __restrict__ work_list, int* __restrict__ work_count) {
+// Phase 1: fp32 maximum of the surviving window and the round-off bound tau, per (pair, ratio).
+__global__ void __launch_bounds__(256) window_max_kernel(const SelJob* __restrict__ jobs,
+                                                          const float* __restrict__ scores,
+                                                          const float2* __restrict__ job_energy,
+                                                          float2* __restrict__ job_stat) {
   const SelJob job = jobs[blockIdx.x];
   const int tid = threadIdx.x;
   __shared__ float smax[256];
-  __shared__ int scount;
-  __shared__ int swarp[8];
   if (job.kind != 0 || job.m_lo > job.m_hi) {
-    if (tid == 0) cand_cnt[blockIdx.x] = 0;
+    if (tid == 0) job_stat[blockIdx.x] = make_float2(-INFINITY, 0.f);
     return;
   }
   const float* c = scores + job.score_off;
@@ -183,13 +182,47 @@ __global__ void __launch_bounds__(256) select_candidates_kernel(
     if (tid < w) smax[tid] = fmaxf(smax[tid], smax[tid + w]);
     __syncthreads();
   }
-  mx = smax[0];
-  float e2 = 0.f;
-  for (int i = 0; i < job.n_tiles; ++i) {
-    const float2 e = job_energy[job.energy_slot + i];
-    e2 = fmaxf(e2, e.x * e.y);
+  if (tid == 0) {
+    float e2 = 0.f;
+    for (int i = 0; i < job.n_tiles; ++i) {
+      const float2 e = job_energy[job.energy_slot + i];
+      e2 = fmaxf(e2, e.x * e.y);
+    }
+    job_stat[blockIdx.x] = make_float2(smax[0], kTauRel * sqrtf(e2) + 1e-30f);
   }
-  const float cut = mx - (kTauRel * sqrtf(e2) + 1e-30f);
+}
+
+// Phase 2.  With winner_only (b2_sync_batch when only the best ratio is wanted) a (pair, ratio)
+// whose fp32 maximum cannot reach the best ratio's even after round-off (mx + tau < max_k (mx_k -
+// tau_k)) is not re-scored: it reports its fp32 maximum and is flagged B2_ALIGN_APPROX.
+__global__ void __launch_bounds__(256) select_candidates_kernel(
+    const SelJob* __restrict__ jobs, const float* __restrict__ scores,
+    const float2* __restrict__ job_stat, int K, int winner_only, int* __restrict__ cand_off,
+    int* __restrict__ cand_cnt, int* __restrict__ work_list, int* __restrict__ work_count) {
+  const SelJob job = jobs[blockIdx.x];
+  const int tid = threadIdx.x;
+  __shared__ int scount;
+  __shared__ int swarp[8];
+  if (job.kind != 0 || job.m_lo > job.m_hi) {
+    if (tid == 0) cand_cnt[blockIdx.x] = 0;
+    return;
+  }
+  const float* c = scores + job.score_off;
+  const float2 stat = job_stat[blockIdx.x];
+  float cut = stat.x - stat.y;
+  bool approx_only = false;
+  if (winner_only) {
+    const int b0 = (blockIdx.x / K) * K;
+    float best_floor = -INFINITY;
+    for (int k = 0; k < K; ++k) {
+      const float2 s = job_stat[b0 + k];
+      best_floor = fmaxf(best_floor, s.x - s.y);
+    }
+    if (stat.x + stat.y < best_floor) {  // cannot win: keep only the fp32 argmax (largest offset)
+      approx_only = true;
+      cut = stat.x;
+    }
+  }
   if (tid == 0) scount = 0;
   __syncthreads();
   // walk m from high to low so that slots fill in order of increasing index m_hi - m ... wait:
@@ -211,6 +244,10 @@ __global__ void __launch_bounds__(256) select_candidates_kernel(
       scount += tot;
     }
     __syncthreads();
+  }
+  if (approx_only) {  // slot 0 holds the largest offset attaining the fp32 maximum
+    if (tid == 0) cand_cnt[blockIdx.x] = -1;
+    return;
   }
   if (tid == 0) {
     cand_cnt[blockIdx.x] = scount;
@@ -247,7 +284,19 @@ __global__ void __launch_bounds__(256) rescore_kernel(const SelJob* __restrict__
     const int per = (len + kRescoreSeg - 1) / kRescoreSeg;
     const int a0 = j_lo + seg * per, a1 = min(j_hi, a0 + per);
     double acc = 0.0;
-    for (int i = a0 + threadIdx.x; i < a1; i += 256) {
+    int i = a0 + threadIdx.x;
+    for (; i + 3 * 256 < a1; i += 4 * 256) {  // 8 independent loads in flight per thread
+      float sv[4], rv[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        sv[u] = __ldg(s + i + u * 256);
+        rv[u] = __ldg(r + i + u * 256 + o);
+      }
+#pragma unroll
+      for (int u = 0; u < 4; ++u)
+        acc = fma(2.0 * (double)sv[u] - 1.0, 2.0 * (double)rv[u] - 1.0, acc);
+    }
+    for (; i < a1; i += 256) {
       const double a = 2.0 * (double)__ldg(s + i) - 1.0;
       const double b = 2.0 * (double)__ldg(r + i + o) - 1.0;
       acc = fma(a, b, acc);
@@ -267,6 +316,7 @@ __global__ void __launch_bounds__(128) pick_kernel(const SelJob* __restrict__ jo
                                                     const int* __restrict__ cand_off,
                                                     const int* __restrict__ cand_cnt,
                                                     const double* __restrict__ cand_partial,
+                                                    const float2* __restrict__ job_stat,
                                                     double* __restrict__ score,
                                                     int32_t* __restrict__ offset,
                                                     int32_t* __restrict__ status) {
@@ -286,6 +336,12 @@ __global__ void __launch_bounds__(128) pick_kernel(const SelJob* __restrict__ jo
     return;
   }
   const int cnt = cand_cnt[j];
+  if (cnt < 0) {  // winner_only: this ratio cannot win, fp32 result reported
+    score[job.out_index] = (double)job_stat[j].x;
+    offset[job.out_index] = cand_off[(size_t)j * kCandMax];
+    status[job.out_index] = B2_ALIGN_APPROX;
+    return;
+  }
   const int n = min(cnt, kCandMax);
   double bs = -INFINITY;
   int bo = 0;
@@ -322,7 +378,7 @@ long long floor_div(long long a, long long b) {
 
 int b2i_align_launch(b2_ctx* h, const float* d_ref, const int64_t* ref_off, const float* d_sub,
                      const int64_t* sub_off, int B, int K, int32_t max_offset_samples,
-                     double* d_score, int32_t* d_offset, int32_t* d_status) {
+                     double* d_score, int32_t* d_offset, int32_t* d_status, int winner_only) {
   const size_t J = (size_t)B * K;
   std::vector<SelJob> sel(J);
   struct PairPlan { long long o_min, o_max; int n_tiles; bool any; };
@@ -405,9 +461,10 @@ int b2i_align_launch(b2_ctx* h, const float* d_ref, const int64_t* ref_off, cons
                 &d_scores));
   float* scores = (float*)d_scores;
   float2* job_energy = (float2*)((char*)d_scores + (((size_t)(score_total + 16) * 4 + 7) & ~size_t(7)));
-  B2_TRY(b2i_ws(h, b2_ctx::WS_CAND, J * kCandMax * (8 * kRescoreSeg + 8) + J * 4 + 64, &d_cand));
+  B2_TRY(b2i_ws(h, b2_ctx::WS_CAND, J * kCandMax * (8 * kRescoreSeg + 8) + J * 12 + 64, &d_cand));
   double* cand_partial = (double*)d_cand;
-  int* cand_off = (int*)(cand_partial + J * kCandMax * kRescoreSeg);
+  float2* job_stat = (float2*)(cand_partial + J * kCandMax * kRescoreSeg);
+  int* cand_off = (int*)(job_stat + J);
   int* cand_cnt = cand_off + J * kCandMax;
   int* work_list = cand_cnt + J;
   int* work_count = work_list + J * kCandMax;
@@ -496,15 +553,17 @@ int b2i_align_launch(b2_ctx* h, const float* d_ref, const int64_t* ref_off, cons
   B2_TRY(b2i_meta_commit(&a));
   if (J >= (1u << 26)) B2_FAIL(h, B2_ERR_UNSUPPORTED, "align: B*K too large for one call");
   B2_CUDA(h, cudaMemsetAsync(work_count, 0, sizeof(int), h->stream));
-  select_candidates_kernel<<<(unsigned)J, 256, 0, h->stream>>>(d_sel, scores, job_energy, cand_off,
-                                                                cand_cnt, work_list, work_count);
+  window_max_kernel<<<(unsigned)J, 256, 0, h->stream>>>(d_sel, scores, job_energy, job_stat);
+  B2_CHECK_LAUNCH(h, "window_max_kernel");
+  select_candidates_kernel<<<(unsigned)J, 256, 0, h->stream>>>(d_sel, scores, job_stat, K, winner_only,
+                                                                cand_off, cand_cnt, work_list, work_count);
   B2_CHECK_LAUNCH(h, "select_candidates_kernel");
   rescore_kernel<<<(unsigned)(h->sm_count * 8), 256, 0, h->stream>>>(d_sel, d_ref, d_sub, cand_off,
                                                                       work_list, work_count, cand_partial);
   B2_CHECK_LAUNCH(h, "rescore_kernel");
   pick_kernel<<<(unsigned)((J + 127) / 128), 128, 0, h->stream>>>(d_sel, (int)J, cand_off, cand_cnt,
-                                                                   cand_partial, d_score, d_offset,
-                                                                   d_status);
+                                                                   cand_partial, job_stat, d_score,
+                                                                   d_offset, d_status);
   B2_CHECK_LAUNCH(h, "pick_kernel");
   return B2_OK;
 }

@@ -47,7 +47,9 @@ enum {
   B2_ALIGN_OK = 0,
   B2_ALIGN_EMPTY = 1,        /* reference or subtitle signal has length 0 */
   B2_ALIGN_ALL_MASKED = 2,   /* max_offset mask left nothing: score = -inf, offset = N-1-S */
-  B2_ALIGN_CAND_OVERFLOW = 4 /* more near-maximal candidates than the re-score budget (flag) */
+  B2_ALIGN_CAND_OVERFLOW = 4, /* more near-maximal candidates than the re-score budget (flag) */
+  B2_ALIGN_APPROX = 8 /* b2_sync_batch without per-ratio outputs: this ratio provably cannot be
+                         the pair's best, so it was not re-scored; fp32 score / its argmax kept */
 };
 
 #define B2_MAX_OFFSET_NONE (-1) /* FFTAligner(max_offset_samples=None) */

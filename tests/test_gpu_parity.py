@@ -367,6 +367,11 @@ def test_sync_batch_small_vs_oracle(handle):
         wk = ao.max_score_select(results, 6000)
         assert (bk[b], bo[b]) == (wk, results[wk][1]) == (k, delta)
         assert _score_ok(bs[b], results[wk][0])
+    # winner-only mode (no per-ratio outputs requested): identical best (score, offset, ratio)
+    bs2, bo2, bk2, _, _ = handle.sync_batch(
+        pcm, pcm_off, 16000, 100, 0.0, 100000, -1, -1, np.concatenate(cs), np.concatenate(ce), None,
+        cue_off, grid, 0.0, 6000, want_all=False)
+    assert np.array_equal(bs2, bs) and np.array_equal(bo2, bo) and np.array_equal(bk2, bk)
 
 
 def test_sync_two_hour_pair_recovers_offset(handle):
