@@ -117,7 +117,10 @@ def run_gpu(args):
     bs = BatchSynchronizer(ratios, FRAME_RATE, SAMPLE_RATE, 0.0, max_offset_seconds=MAX_OFFSET_SECONDS,
                            device=local_rank)
     h = bs.handle
-    stream = torch.cuda.current_stream()
+    # everything (our kernels, torch ops, NCCL) is ordered on one explicit stream, and that is the
+    # stream the timing events are recorded on
+    stream = torch.cuda.Stream(device=dev)
+    torch.cuda.set_stream(stream)
     bs.use_torch_stream()
 
     # ---- synthetic inputs (untimed): masks on the host, PCM synthesised on the device --------

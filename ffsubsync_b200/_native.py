@@ -127,6 +127,10 @@ class Handle:
 
     # -- plumbing ---------------------------------------------------------------------------
     def set_stream(self, cuda_stream: Optional[int]):
+        """cuda_stream: a cudaStream_t handle as int (e.g. torch.cuda.Stream().cuda_stream);
+        0 means the legacy default stream (torch's default), None gives the handle its own stream."""
+        if cuda_stream is not None and int(cuda_stream) == 0:
+            cuda_stream = 1  # cudaStreamLegacy: NULL would mean "own stream" in the C ABI
         self._check(self.lib.b2_set_stream(self.h, cuda_stream), "b2_set_stream")
 
     def synchronize(self):

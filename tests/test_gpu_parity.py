@@ -74,6 +74,31 @@ def test_vad_full_scale_samples(handle):
     assert np.array_equal(out.astype(np.float64), vo.energy_zcr_detect(pcm, 100, 16000, 0.0, 100000, 0, 160))
 
 
+def test_device_memspace_is_ordered_on_the_callers_stream(handle):
+    """B2_DEVICE calls only enqueue work on the stream given to b2_set_stream; torch ops queued on
+    the same stream right after must see the results (no host synchronisation in between).  Covers
+    an explicit torch stream and torch's default stream (handle 0 -> cudaStreamLegacy)."""
+    import torch
+    from ffsubsync_b200 import _native
+    cls = np.random.RandomState(9).randint(0, 3, 200000).astype(np.uint8)
+    want = vo.energy_zcr_detect(vo.synth_pcm(cls, 160, seed=4), 100, 16000, 0.0)
+    try:
+        for stream in (torch.cuda.Stream(), torch.cuda.default_stream()):
+            with torch.cuda.stream(stream):
+                handle.set_stream(stream.cuda_stream)
+                cls_d = torch.from_numpy(cls).cuda()
+                pcm = torch.empty(len(cls) * 160, dtype=torch.int16, device="cuda")
+                out = torch.full((len(cls),), -7.0, dtype=torch.float32, device="cuda")
+                handle.synth_pcm(cls_d.data_ptr(), len(cls), 160, 4, out=pcm.data_ptr(), memspace=_native.B2_DEVICE)
+                handle.vad_energy_zcr(pcm.data_ptr(), [0, pcm.numel()], 16000, 100, 0.0, 100000,
+                                      out=out.data_ptr(), memspace=_native.B2_DEVICE)
+                total = out.double().sum()      # queued behind our kernels on the same stream
+                got = out.cpu().numpy()
+            assert np.array_equal(got.astype(np.float64), want) and float(total) == want.sum()
+    finally:
+        handle.set_stream(None)
+
+
 def test_synth_pcm_matches_numpy_replay(handle):
     cls = np.random.RandomState(2).randint(0, 3, 500).astype(np.uint8)
     got = handle.synth_pcm(cls, len(cls), 160, seed=77)
