@@ -43,6 +43,8 @@ extern "C" int b2_create(int device, b2_handle* out) {
   }
   h->own_stream = true;
   h->log2_quirk_mask = compute_log2_quirk_mask();
+  const char* acc = getenv("B2_ACC");  // A/B switch for profiling: "reg" keeps the accumulators in registers
+  h->acc_in_tmem = !(acc && strcmp(acc, "reg") == 0);
   *out = h;
   return B2_OK;
 }
@@ -144,14 +146,20 @@ int b2i_meta_begin(b2_ctx* h, MetaArena* a, size_t bytes) {
   b2_ctx::MetaSlot& s = h->meta[slot];
   if (!s.ev) B2_CUDA(h, cudaEventCreateWithFlags(&s.ev, cudaEventDisableTiming));
   if (bytes > s.cap) {
-    if (s.d) B2_CUDA(h, cudaFree(s.d));
-    if (s.p) B2_CUDA(h, cudaFreeHost(s.p));
-    s.d = s.p = nullptr;
-    s.cap = 0;
-    const size_t want = bytes + bytes / 4 + 4096;
-    B2_CUDA(h, cudaMalloc(&s.d, want));
-    B2_CUDA(h, cudaMallocHost(&s.p, want));
-    s.cap = want;
+    // grow every slot at once (pinned allocations cost milliseconds): after the first large
+    // call no later arena, whichever slot it lands on, allocates again
+    B2_CUDA(h, cudaStreamSynchronize(h->stream));
+    const size_t want = bytes + bytes / 4 + 65536;
+    for (auto& m : h->meta) {
+      if (m.cap >= want) continue;
+      if (m.d) B2_CUDA(h, cudaFree(m.d));
+      if (m.p) B2_CUDA(h, cudaFreeHost(m.p));
+      m.d = m.p = nullptr;
+      m.cap = 0;
+      B2_CUDA(h, cudaMalloc(&m.d, want));
+      B2_CUDA(h, cudaMallocHost(&m.p, want));
+      m.cap = want;
+    }
   }
   a->slot = slot;
   a->dbase = (char*)s.d;

@@ -445,7 +445,22 @@ CORR_HD void spec_store(const float2* buf, const Tables& t, int tid, float4* spe
   }
 }
 
+// conj(A) * B for the thread's pair slot u: A from the subtitle block spectrum in buf, B = b.
+CORR_HD void product_terms(const float2* buf, const Tables& t, int tid, int u, float4 b, float2& dp,
+                           float2& dq) {
+  float2 hp, hq;
+  untangle_slot(buf, t, tid + u * kThreads, hp, hq);
+  if (u == 0 && tid == 0) {
+    dp = make_float2(hp.x * b.x, hp.y * b.y);  // two real bins: DC and Nyquist
+  } else {
+    dp = cmul_conj_a(hp, make_float2(b.x, b.y));
+  }
+  dq = cmul_conj_a(hq, make_float2(b.z, b.w));
+}
+
 // Consumer: acc += conj(A) * B for the subtitle block spectrum in buf and the stored B.
+// (Register-accumulator form; the device kernel keeps the accumulators in tensor memory instead,
+// see sub_correlate_kernel - this form is what tests/host_emul runs.)
 CORR_HD void sub_accumulate(SubState& st, const float2* buf, const Tables& t, int tid,
                             const float4* spec) {
   // the stored reference spectrum is read two slots ahead of its use (L2 latency)
@@ -457,15 +472,8 @@ CORR_HD void sub_accumulate(SubState& st, const float2* buf, const Tables& t, in
     const float4 b = b0;
     b0 = b1;
     if (u + 2 < 16) b1 = CORR_LDG(spec + r + 2 * kThreads);
-    float2 hp, hq;
-    untangle_slot(buf, t, r, hp, hq);
-    float2 dp;
-    if (u == 0 && tid == 0) {
-      dp = make_float2(hp.x * b.x, hp.y * b.y);  // two real bins: DC and Nyquist
-    } else {
-      dp = cmul_conj_a(hp, make_float2(b.x, b.y));
-    }
-    const float2 dq = cmul_conj_a(hq, make_float2(b.z, b.w));
+    float2 dp, dq;
+    product_terms(buf, t, tid, u, b, dp, dq);
     st.cp[u] = cadd(st.cp[u], dp);
     st.cq[u] = cadd(st.cq[u], dq);
   }
