@@ -42,6 +42,16 @@ extern "C" int b2_create(int device, b2_handle* out) {
     return B2_ERR_CUDA;
   }
   h->own_stream = true;
+  if (cudaStreamCreateWithFlags(&h->stream2, cudaStreamNonBlocking) != cudaSuccess) {
+    cudaStreamDestroy(h->stream);
+    delete h;
+    return B2_ERR_CUDA;
+  }
+  for (auto& e : h->ev_pool)
+    if (cudaEventCreateWithFlags(&e, cudaEventDisableTiming) != cudaSuccess) {
+      delete h;
+      return B2_ERR_CUDA;
+    }
   h->log2_quirk_mask = compute_log2_quirk_mask();
   const char* acc = getenv("B2_ACC");  // A/B switch for profiling: "reg" keeps the accumulators in registers
   h->acc_in_tmem = !(acc && strcmp(acc, "reg") == 0);
@@ -57,11 +67,16 @@ extern "C" int b2_destroy(b2_handle h) {
     if (w.p) cudaFree(w.p);
   for (auto& p : h->pinned)
     if (p.p) cudaFreeHost(p.p);
-  for (auto& m : h->meta) {
-    if (m.d) cudaFree(m.d);
-    if (m.p) cudaFreeHost(m.p);
-    if (m.ev) cudaEventDestroy(m.ev);
-  }
+  if (h->stream2) cudaStreamSynchronize(h->stream2);
+  for (auto& ring : h->meta)
+    for (auto& m : ring) {
+      if (m.d) cudaFree(m.d);
+      if (m.p) cudaFreeHost(m.p);
+      if (m.ev) cudaEventDestroy(m.ev);
+    }
+  for (auto& e : h->ev_pool)
+    if (e) cudaEventDestroy(e);
+  if (h->stream2) cudaStreamDestroy(h->stream2);
   if (h->own_stream && h->stream) cudaStreamDestroy(h->stream);
   delete h;
   return B2_OK;
@@ -140,17 +155,20 @@ int b2i_pinned(b2_ctx* h, int which, size_t bytes, void** out) {
 int b2i_meta_begin(b2_ctx* h, MetaArena* a, size_t bytes) {
   a->h = h;
   bytes = (bytes + 255) & ~size_t(255);
-  const int slot = (int)(h->meta_seq % b2_ctx::kMetaSlots);
-  b2_ctx::MetaSlot& next = h->meta[(slot + 1) % b2_ctx::kMetaSlots];
-  if (h->meta_seq >= (uint64_t)b2_ctx::kMetaSlots && next.ev) B2_CUDA(h, cudaEventSynchronize(next.ev));
-  b2_ctx::MetaSlot& s = h->meta[slot];
+  b2_ctx::MetaSlot* ring = h->meta[h->ring];
+  uint64_t& seq = h->meta_seq[h->ring];
+  const int slot = (int)(seq % b2_ctx::kMetaSlots);
+  b2_ctx::MetaSlot& next = ring[(slot + 1) % b2_ctx::kMetaSlots];
+  if (seq >= (uint64_t)b2_ctx::kMetaSlots && next.ev) B2_CUDA(h, cudaEventSynchronize(next.ev));
+  b2_ctx::MetaSlot& s = ring[slot];
   if (!s.ev) B2_CUDA(h, cudaEventCreateWithFlags(&s.ev, cudaEventDisableTiming));
   if (bytes > s.cap) {
-    // grow every slot at once (pinned allocations cost milliseconds): after the first large
-    // call no later arena, whichever slot it lands on, allocates again
+    // grow every slot of this ring at once (pinned allocations cost milliseconds): after the
+    // first large call no later arena, whichever slot it lands on, allocates again
     B2_CUDA(h, cudaStreamSynchronize(h->stream));
     const size_t want = bytes + bytes / 4 + 65536;
-    for (auto& m : h->meta) {
+    for (int i = 0; i < b2_ctx::kMetaSlots; ++i) {
+      b2_ctx::MetaSlot& m = ring[i];
       if (m.cap >= want) continue;
       if (m.d) B2_CUDA(h, cudaFree(m.d));
       if (m.p) B2_CUDA(h, cudaFreeHost(m.p));
@@ -162,11 +180,12 @@ int b2i_meta_begin(b2_ctx* h, MetaArena* a, size_t bytes) {
     }
   }
   a->slot = slot;
+  a->ring = h->ring;
   a->dbase = (char*)s.d;
   a->hbase = (char*)s.p;
   a->cap = bytes;
   a->used = 0;
-  h->meta_seq++;
+  seq++;
   return B2_OK;
 }
 
@@ -189,8 +208,29 @@ int b2i_meta_commit(MetaArena* a) {
   b2_ctx* h = a->h;
   if (a->used)
     B2_CUDA(h, cudaMemcpyAsync(a->dbase, a->hbase, a->used, cudaMemcpyHostToDevice, h->stream));
-  B2_CUDA(h, cudaEventRecord(h->meta[a->slot].ev, h->stream));
+  B2_CUDA(h, cudaEventRecord(h->meta[a->ring][a->slot].ev, h->stream));
   return B2_OK;
+}
+
+// Run `body` with the handle temporarily launching on its internal second stream.
+struct Stream2Scope {
+  b2_ctx* h;
+  cudaStream_t saved;
+  int saved_ring;
+  explicit Stream2Scope(b2_ctx* hh) : h(hh), saved(hh->stream), saved_ring(hh->ring) {
+    h->stream = h->stream2;
+    h->ring = 1;
+  }
+  ~Stream2Scope() {
+    h->stream = saved;
+    h->ring = saved_ring;
+  }
+};
+
+static cudaEvent_t next_event(b2_ctx* h) {
+  cudaEvent_t e = h->ev_pool[h->ev_next];
+  h->ev_next = (h->ev_next + 1) % b2_ctx::kEvents;
+  return e;
 }
 
 // ---- helpers for B2_HOST calls -------------------------------------------------------------
@@ -508,24 +548,62 @@ extern "C" int b2_sync_batch(b2_handle h, const int16_t* pcm, const int64_t* pcm
     B2_TRY(stage_in(h, b2_ctx::WS_STAGE_IN0, pcm, (size_t)pcm_off[B] * 2, &dp));
     d_pcm = (const int16_t*)dp;
   }
-  B2_TRY(b2i_vad_launch(h, d_pcm, pcm_off, B, fpw, non_speech_label, energy_threshold, z_lo, z_hi,
-                        (float*)d_refsig, ref_off.data()));
-  B2_TRY(b2i_raster_launch(h, cue_start_s, cue_end_s, cue_keep, cue_off, B, ratios, K, 0, nullptr,
-                           sample_rate, start_seconds, (float*)d_subsig, sub_off.data()));
   double* o_score = (memspace == B2_DEVICE && all_score) ? all_score : d_score;
   int32_t* o_offset = (memspace == B2_DEVICE && all_offset) ? all_offset : d_offset;
+  double* o_bs = memspace == B2_DEVICE ? best_score : d_bs;
+  int32_t* o_bo = memspace == B2_DEVICE ? best_offset : d_bo;
+  int32_t* o_bk = memspace == B2_DEVICE ? best_k : d_bk;
   // only the best ratio of each pair is reported unless the per-ratio arrays are requested:
   // ratios that provably cannot win are then not re-scored exactly (B2_ALIGN_APPROX)
   const int winner_only = (!all_score && !all_offset) ? 1 : 0;
-  B2_TRY(b2i_align_launch(h, (const float*)d_refsig, ref_off.data(), (const float*)d_subsig,
-                          sub_off.data(), B, K, max_offset_samples, o_score, o_offset, d_status,
-                          winner_only));
-  if (memspace == B2_DEVICE) {
-    B2_TRY(b2i_reduce_launch(h, o_score, o_offset, d_status, B, K, max_offset_samples, best_score,
-                             best_offset, best_k));
-    return B2_OK;
+
+  // Software pipeline over sub-batches of pairs: the VAD of sub-batch i+1 (HBM-bound, caller's
+  // stream) runs while sub-batch i is rasterised / correlated / reduced (FP32- and shared-memory
+  // bound, internal stream2).  The two kernels are sized to co-reside on an SM (VAD: 82 KB smem,
+  // 9 K registers; correlation: 139 KB, 48 K registers, accumulators in tensor memory).
+  // Sub-batches stay >= ~1.5 waves of correlation jobs so the correlation grid keeps the SMs busy.
+  int n_sub = (int)std::min<int64_t>(4, ((int64_t)B * K) / (3 * (int64_t)h->sm_count / 2));
+  if (n_sub < 1) n_sub = 1;
+  const char* ns_env = getenv("B2_SUBBATCHES");
+  if (ns_env) n_sub = std::max(1, std::min(B, atoi(ns_env)));
+  // make sure the workspaces that stream2 grows are not reallocated under the other stream
+  cudaEvent_t done2 = nullptr;
+  for (int i = 0; i < n_sub; ++i) {
+    const int b0 = (int)((int64_t)B * i / n_sub), b1 = (int)((int64_t)B * (i + 1) / n_sub);
+    if (b1 == b0) continue;
+    const int nb = b1 - b0;
+    B2_TRY(b2i_vad_launch(h, d_pcm, pcm_off + b0, nb, fpw, non_speech_label, energy_threshold, z_lo,
+                          z_hi, (float*)d_refsig, ref_off.data() + b0));
+    if (n_sub == 1) {
+      B2_TRY(b2i_raster_launch(h, cue_start_s, cue_end_s, cue_keep, cue_off, B, ratios, K, 0, nullptr,
+                               sample_rate, start_seconds, (float*)d_subsig, sub_off.data()));
+      B2_TRY(b2i_align_launch(h, (const float*)d_refsig, ref_off.data(), (const float*)d_subsig,
+                              sub_off.data(), B, K, max_offset_samples, o_score, o_offset, d_status,
+                              winner_only));
+      B2_TRY(b2i_reduce_launch(h, o_score, o_offset, d_status, B, K, max_offset_samples, o_bs, o_bo,
+                               o_bk));
+      break;
+    }
+    cudaEvent_t vad_done = next_event(h);
+    B2_CUDA(h, cudaEventRecord(vad_done, h->stream));
+    {
+      Stream2Scope on2(h);
+      B2_CUDA(h, cudaStreamWaitEvent(h->stream, vad_done, 0));
+      const size_t j0 = (size_t)b0 * K;
+      B2_TRY(b2i_raster_launch(h, cue_start_s, cue_end_s, cue_keep, cue_off + b0, nb, ratios, K, 0,
+                               nullptr, sample_rate, start_seconds, (float*)d_subsig,
+                               sub_off.data() + j0));
+      B2_TRY(b2i_align_launch(h, (const float*)d_refsig, ref_off.data() + b0, (const float*)d_subsig,
+                              sub_off.data() + j0, nb, K, max_offset_samples, o_score + j0,
+                              o_offset + j0, d_status + j0, winner_only));
+      B2_TRY(b2i_reduce_launch(h, o_score + j0, o_offset + j0, d_status + j0, nb, K,
+                               max_offset_samples, o_bs + b0, o_bo + b0, o_bk + b0));
+      done2 = next_event(h);
+      B2_CUDA(h, cudaEventRecord(done2, h->stream));
+    }
   }
-  B2_TRY(b2i_reduce_launch(h, o_score, o_offset, d_status, B, K, max_offset_samples, d_bs, d_bo, d_bk));
+  if (done2) B2_CUDA(h, cudaStreamWaitEvent(h->stream, done2, 0));  // caller's stream sees everything
+  if (memspace == B2_DEVICE) return B2_OK;
   B2_TRY(copy_out(h, best_score, d_bs, (size_t)B * 8));
   B2_TRY(copy_out(h, best_offset, d_bo, (size_t)B * 4));
   B2_TRY(copy_out(h, best_k, d_bk, (size_t)B * 4));

@@ -33,7 +33,7 @@ struct b2_ctx {
   int acc_in_tmem = 1;           // correlation accumulators in tensor memory (B2_ACC=reg: registers)
   // named grow-only workspaces
   enum { WS_STAGE_IN0, WS_STAGE_IN1, WS_STAGE_OUT, WS_META, WS_SPEC, WS_SCORES, WS_CAND,
-         WS_SIG_REF, WS_SIG_SUB, WS_MISC, WS_COUNT };
+         WS_SIG_REF, WS_SIG_SUB, WS_MISC, WS_COUNTERS, WS_COUNT };
   DeviceBuf ws[WS_COUNT];
   HostBuf pinned[4];
   // ring of metadata upload buffers (see b2i_meta_begin)
@@ -44,8 +44,16 @@ struct b2_ctx {
     size_t cap = 0;
     cudaEvent_t ev = nullptr;
   };
-  MetaSlot meta[kMetaSlots];
-  uint64_t meta_seq = 0;
+  // one ring per stream the handle launches on (the in-order reuse argument is per stream)
+  MetaSlot meta[2][kMetaSlots];
+  uint64_t meta_seq[2] = {0, 0};
+  int ring = 0;                    // ring in use: 0 = caller-facing stream, 1 = internal stream2
+  // b2_sync_batch overlaps the VAD of sub-batch i+1 (stream) with the alignment of sub-batch i
+  // (stream2); events from a small pool order the two
+  cudaStream_t stream2 = nullptr;
+  static const int kEvents = 16;
+  cudaEvent_t ev_pool[kEvents] = {};
+  int ev_next = 0;
 };
 
 #define B2_FAIL(h, code, ...)                          \
@@ -86,7 +94,7 @@ struct MetaArena {
   char* dbase = nullptr;
   char* hbase = nullptr;
   size_t cap = 0, used = 0;
-  int slot = 0;
+  int slot = 0, ring = 0;
 };
 int b2i_meta_begin(b2_ctx* h, MetaArena* a, size_t bytes);
 void* b2i_meta_put(MetaArena* a, const void* src, size_t bytes);  // returns device pointer

@@ -134,15 +134,18 @@ int b2i_raster_launch(b2_ctx* h, const double* cue_start, const double* cue_end,
                       const uint8_t* cue_keep, const int64_t* cue_off, int B, const double* ratios,
                       int K, int per_pair_ratios, const double* levels, int sample_rate,
                       double start_seconds, float* d_out, const int64_t* out_off) {
+  // cue_off / out_off may be slices of larger tables (sub-batches): entries are absolute indices
+  // into cue_start/... and d_out, only [cue_off[0], cue_off[B]) is uploaded (pointers rebased)
   const size_t J = (size_t)B * K;
-  const size_t ncue = (size_t)cue_off[B];
+  const size_t c0 = (size_t)cue_off[0];
+  const size_t ncue = (size_t)cue_off[B] - c0;
   const size_t nr = per_pair_ratios ? J : (size_t)K;
   MetaArena a;
   B2_TRY(b2i_meta_begin(h, &a, ncue * 17 + (B + 1) * 8 + (J + 1) * 8 + nr * 16 + 1024));
   RasterParams p;
-  p.start_s = (const double*)b2i_meta_put(&a, cue_start, ncue * 8);
-  p.end_s = (const double*)b2i_meta_put(&a, cue_end, ncue * 8);
-  p.keep = cue_keep ? (const uint8_t*)b2i_meta_put(&a, cue_keep, ncue) : nullptr;
+  p.start_s = (const double*)b2i_meta_put(&a, cue_start + c0, ncue * 8) - c0;
+  p.end_s = (const double*)b2i_meta_put(&a, cue_end + c0, ncue * 8) - c0;
+  p.keep = cue_keep ? (const uint8_t*)b2i_meta_put(&a, cue_keep + c0, ncue) - c0 : nullptr;
   p.cue_off = (const long long*)b2i_meta_put(&a, cue_off, (size_t)(B + 1) * 8);
   p.ratios = (const double*)b2i_meta_put(&a, ratios, nr * 8);
   p.levels = levels ? (const double*)b2i_meta_put(&a, levels, nr * 8) : nullptr;
@@ -154,8 +157,8 @@ int b2i_raster_launch(b2_ctx* h, const double* cue_start, const double* cue_end,
   p.per_pair = per_pair_ratios;
   p.sample_rate = sample_rate;
   p.start_seconds = start_seconds;
-  const size_t total = (size_t)out_off[J];
-  if (total) B2_CUDA(h, cudaMemsetAsync(d_out, 0, total * 4, h->stream));
+  const size_t total = (size_t)(out_off[J] - out_off[0]);
+  if (total) B2_CUDA(h, cudaMemsetAsync(d_out + out_off[0], 0, total * 4, h->stream));
   int64_t max_cues = 0;
   for (int b = 0; b < B; ++b) max_cues = std::max<int64_t>(max_cues, cue_off[b + 1] - cue_off[b]);
   if (max_cues == 0 || J == 0) return B2_OK;

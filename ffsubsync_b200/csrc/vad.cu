@@ -38,6 +38,7 @@ struct VadParams {
   const long long* pcm_off;   // [B+1] samples
   const long long* out_off;   // [B+1] windows
   const long long* tile_off;  // [B+1] tiles
+  unsigned long long* tile_counter;  // zeroed before the launch
   long long total_tiles;
   long long pcm_total_bytes;
   long long e_min;            // fpw * energy_threshold
@@ -151,7 +152,6 @@ __global__ void __launch_bounds__(kThreads) vad_energy_zcr_kernel(VadParams p) {
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   __syncthreads();
-  const long long first = blockIdx.x, stride = gridDim.x;
 
   if (tid >= kConsumerThreads) {
     // ================================ producer warp ==========================================
@@ -160,7 +160,9 @@ __global__ void __launch_bounds__(kThreads) vad_energy_zcr_kernel(VadParams p) {
     for (long long it = 0;; ++it) {
       const int stage = (int)(it % nst);
       if (it >= nst) mbar_wait(&empty_bar[stage], (uint32_t)(((it / nst) - 1) & 1));
-      const long long t = first + it * stride;
+      // dynamic tile hand-out: whichever CTAs are resident share the stream evenly, also when
+      // this kernel co-runs with the correlation kernels and gets fewer than its 2 CTAs per SM
+      const long long t = (long long)atomicAdd(p.tile_counter, 1ULL);
       TileDesc d;
       if (t >= p.total_tiles) {
         d.n_windows = 0;
@@ -366,6 +368,10 @@ int b2i_vad_launch(b2_ctx* h, const int16_t* d_pcm, const int64_t* pcm_off, int 
   p.z_hi = z_hi;
   p.label = non_speech_label;
 
+  void* d_counter;
+  B2_TRY(b2i_ws(h, b2_ctx::WS_COUNTERS, 64, &d_counter));
+  p.tile_counter = (unsigned long long*)d_counter;
+  B2_CUDA(h, cudaMemsetAsync(d_counter, 0, 8, h->stream));
   B2_CUDA(h, cudaFuncSetAttribute(vad_energy_zcr_kernel,
                                   cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   int per_sm = (int)std::max<size_t>(1, std::min<size_t>(4, (220 * 1024) / smem));
