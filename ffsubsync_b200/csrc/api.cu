@@ -572,8 +572,17 @@ extern "C" int b2_sync_batch(b2_handle h, const int16_t* pcm, const int64_t* pcm
     const int b0 = (int)((int64_t)B * i / n_sub), b1 = (int)((int64_t)B * (i + 1) / n_sub);
     if (b1 == b0) continue;
     const int nb = b1 - b0;
-    B2_TRY(b2i_vad_launch(h, d_pcm, pcm_off + b0, nb, fpw, non_speech_label, energy_threshold, z_lo,
-                          z_hi, (float*)d_refsig, ref_off.data() + b0));
+    {
+      // the first sub-batch has nothing to overlap with: full VAD occupancy; later ones leave
+      // room for the correlation CTAs of the previous sub-batch
+      const char* vc = getenv("B2_VAD_CTAS");
+      h->vad_ctas_per_sm = (n_sub > 1 && i > 0) ? (vc ? atoi(vc) : 1) : 0;
+      const int st = b2i_vad_launch(h, d_pcm, pcm_off + b0, nb, fpw, non_speech_label,
+                                    energy_threshold, z_lo, z_hi, (float*)d_refsig,
+                                    ref_off.data() + b0);
+      h->vad_ctas_per_sm = 0;
+      if (st != B2_OK) return st;
+    }
     if (n_sub == 1) {
       B2_TRY(b2i_raster_launch(h, cue_start_s, cue_end_s, cue_keep, cue_off, B, ratios, K, 0, nullptr,
                                sample_rate, start_seconds, (float*)d_subsig, sub_off.data()));

@@ -62,7 +62,7 @@ __device__ __forceinline__ void l2_prefetch(const void* p, uint32_t bytes) {
 }
 
 // ------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(kThreads, 1)
+__global__ void __maxnreg__(96)  // leaves registers for a co-resident VAD CTA (see sub_correlate_kernel)
     ref_spectra_kernel(const float* __restrict__ ref, const SpecItem* __restrict__ items,
                        float4* __restrict__ spec, float* __restrict__ spec_energy) {
   extern __shared__ __align__(16) unsigned char smem_raw[];

@@ -397,6 +397,18 @@ def test_sync_batch_small_vs_oracle(handle):
         pcm, pcm_off, 16000, 100, 0.0, 100000, -1, -1, np.concatenate(cs), np.concatenate(ce), None,
         cue_off, grid, 0.0, 6000, want_all=False)
     assert np.array_equal(bs2, bs) and np.array_equal(bo2, bo) and np.array_equal(bk2, bk)
+    # sub-batch pipeline (VAD of sub-batch i+1 overlapping the alignment of sub-batch i on a second
+    # stream) forced on this small batch: bit-identical results, per-ratio outputs included
+    import os
+    for n_sub in ("2", "3", "4"):
+        os.environ["B2_SUBBATCHES"] = n_sub
+        try:
+            r = handle.sync_batch(pcm, pcm_off, 16000, 100, 0.0, 100000, -1, -1, np.concatenate(cs),
+                                  np.concatenate(ce), None, cue_off, grid, 0.0, 6000, want_all=True)
+        finally:
+            del os.environ["B2_SUBBATCHES"]
+        assert np.array_equal(r[0], bs) and np.array_equal(r[1], bo) and np.array_equal(r[2], bk)
+        assert np.array_equal(r[3], a_s) and np.array_equal(r[4], a_o)
 
 
 def test_sync_two_hour_pair_recovers_offset(handle):
