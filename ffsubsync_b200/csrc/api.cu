@@ -561,9 +561,12 @@ extern "C" int b2_sync_batch(b2_handle h, const int16_t* pcm, const int64_t* pcm
   // stream) runs while sub-batch i is rasterised / correlated / reduced (FP32- and shared-memory
   // bound, internal stream2).  The two kernels are sized to co-reside on an SM (VAD: 82 KB smem,
   // 9 K registers; correlation: 139 KB, 48 K registers, accumulators in tensor memory).
-  // Sub-batches stay >= ~1.5 waves of correlation jobs so the correlation grid keeps the SMs busy.
-  int n_sub = (int)std::min<int64_t>(4, ((int64_t)B * K) / (3 * (int64_t)h->sm_count / 2));
-  if (n_sub < 1) n_sub = 1;
+  // Measured on B200 (tools/overlap_probe.py, profiles/README.md): the VAD needs both of its CTAs
+  // per SM (16 consumer warps) to reach 5.9 TB/s - with one CTA it runs at 58 % - so sharing the
+  // SM costs more than the overlap returns (148 pairs: 9.55 ms unpipelined, 11.6 ms with 3
+  // sub-batches).  The pipeline therefore stays OFF by default (n_sub = 1); B2_SUBBATCHES=n enables
+  // it for experiments and tests/test_gpu_parity.py keeps it bit-identical.
+  int n_sub = 1;
   const char* ns_env = getenv("B2_SUBBATCHES");
   if (ns_env) n_sub = std::max(1, std::min(B, atoi(ns_env)));
   // make sure the workspaces that stream2 grows are not reallocated under the other stream

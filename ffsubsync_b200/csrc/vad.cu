@@ -378,6 +378,7 @@ int b2i_vad_launch(b2_ctx* h, const int16_t* d_pcm, const int64_t* pcm_off, int 
   // when the correlation kernels of the previous sub-batch run concurrently (b2_sync_batch
   // pipeline) one VAD CTA per SM leaves room (139 KB smem, 48 K registers) for one of theirs
   if (h->vad_ctas_per_sm > 0) per_sm = std::min(per_sm, h->vad_ctas_per_sm);
+  if (const char* f = getenv("B2_VAD_CTAS_FORCE")) per_sm = std::max(1, atoi(f));  // profiling knob
   long long grid = std::min<long long>(p.total_tiles, (long long)h->sm_count * per_sm);
   vad_energy_zcr_kernel<<<(unsigned)grid, kThreads, smem, h->stream>>>(p);
   B2_CHECK_LAUNCH(h, "vad_energy_zcr_kernel");
