@@ -23,7 +23,7 @@ STATUS_NAMES = {0: "B2_OK", -1: "B2_ERR_BAD_ARG", -2: "B2_ERR_CUDA", -3: "B2_ERR
 EXPORTS = [
     "b2_version", "b2_create", "b2_destroy", "b2_set_stream", "b2_synchronize", "b2_last_error",
     "b2_launch_count", "b2_vad_frames_per_window", "b2_vad_num_windows", "b2_vad_energy_zcr",
-    "b2_rasterize_lengths", "b2_rasterize", "b2_first_last_nonzero", "b2_align_batch",
+    "b2_rasterize_lengths", "b2_rasterize", "b2_blend_signals", "b2_first_last_nonzero", "b2_align_batch",
     "b2_reduce_ratios", "b2_sync_batch", "b2_synth_pcm",
 ]
 
@@ -72,6 +72,7 @@ def load() -> ctypes.CDLL:
         lib.b2_rasterize.argtypes = [_vp, _vp, _vp, _vp, _vp, ctypes.c_int, _vp, ctypes.c_int,
                                      ctypes.c_int, _vp, ctypes.c_int, _f64, _vp, _vp, ctypes.c_int]
         lib.b2_first_last_nonzero.argtypes = [_vp, _vp, _vp, ctypes.c_int, _vp, _vp, ctypes.c_int]
+        lib.b2_blend_signals.argtypes = [_vp, _vp, _vp, _i64, ctypes.c_int, _f64, _f64, _vp, ctypes.c_int]
         lib.b2_align_batch.argtypes = [_vp, _vp, _vp, _vp, _vp, ctypes.c_int, ctypes.c_int, _i32,
                                        _vp, _vp, _vp, ctypes.c_int]
         lib.b2_reduce_ratios.argtypes = [_vp, _vp, _vp, _vp, ctypes.c_int, ctypes.c_int, _i32,
@@ -209,6 +210,19 @@ class Handle:
                                    sample_rate, float(start_seconds), _ptr(out), _ptr(out_off), memspace)
         self._check(st, "b2_rasterize")
         return out, out_off
+
+    def blend_signals(self, a, b, mode: int, wa: float = 0.6, wb: float = 0.4, out=None, n=None,
+                      memspace: int = B2_HOST):
+        """mode 0 = min, 1 = max, 2 = wa*a + wb*b; host arrays are clipped to their common length."""
+        if memspace == B2_HOST:
+            n = min(len(a), len(b))
+            a = np.ascontiguousarray(a[:n], dtype=np.float32)
+            b = np.ascontiguousarray(b[:n], dtype=np.float32)
+            out = np.empty(n, dtype=np.float32)
+        st = self.lib.b2_blend_signals(self.h, _ptr(a), _ptr(b), int(n), int(mode), float(wa), float(wb),
+                                       _ptr(out), memspace)
+        self._check(st, "b2_blend_signals")
+        return out
 
     def first_last_nonzero(self, sig, sig_off, memspace: int = B2_HOST, first=None, last=None):
         sig_off = _i64a(sig_off)

@@ -18,6 +18,18 @@ from . import _native
 from .constants import DEFAULT_ENERGY_THRESHOLD, DEFAULT_MAX_OFFSET_SECONDS, SAMPLE_RATE
 
 
+def load_serialized_speech(paths, non_speech_label: float = 0.0):
+    """Batch ingest of ``--serialize-speech`` / ``--make-test-case`` artefacts (``.npz`` with key
+    "speech", or ``.npy``): each file goes through DeserializeSpeechTransformer
+    (ffsubsync/speech_transformers.py:987-1009: values < 1 become ``non_speech_label``).
+    Returns (signals float32 back to back, offsets int64[B+1]) ready for ``sync_signals``."""
+    from .speech_transformers import DeserializeSpeechTransformer
+    sigs = [np.asarray(DeserializeSpeechTransformer(non_speech_label).fit(p).transform(), dtype=np.float32)
+            for p in paths]
+    off = np.concatenate([[0], np.cumsum([len(s) for s in sigs])]).astype(np.int64)
+    return (np.concatenate(sigs) if sigs else np.zeros(0, np.float32)), off
+
+
 class BatchSynchronizer:
     def __init__(self, ratios: Sequence[float], frame_rate: int = 16000, sample_rate: int = SAMPLE_RATE,
                  non_speech_label: float = 0.0, energy_threshold: int = DEFAULT_ENERGY_THRESHOLD,
@@ -61,6 +73,39 @@ class BatchSynchronizer:
             out["best_offset"].data_ptr(), out["best_k"].data_ptr(), a_s, a_o, memspace=_native.B2_DEVICE)
         assert K == len(self.ratios)
         return out
+
+    def sync_signals(self, ref, ref_off, cue_start, cue_end, cue_off, cue_keep=None):
+        """Same as sync_device but starting from reference speech SIGNALS (100 Hz float32, all pairs
+        back to back; numpy array or CUDA tensor) instead of PCM - the replay path of the
+        reference's test-case bundles: ``ref.npz{"speech"}`` + ``in.srt``
+        (ffsubsync/ffsubsync.py:338-343,639-644; DeserializeSpeechTransformer).
+        Returns (best_score f64[B], best_offset i32[B], best_k i32[B]) as numpy arrays."""
+        import torch
+        h = self.handle
+        ref_off = np.ascontiguousarray(ref_off, dtype=np.int64)
+        B, K = len(ref_off) - 1, len(self.ratios)
+        if isinstance(ref, np.ndarray):
+            ref = torch.from_numpy(np.ascontiguousarray(ref, dtype=np.float32)).cuda()
+        dev = ref.device
+        lengths = h.rasterize_lengths(cue_end, cue_off, self.ratios, K, False, self.sample_rate)
+        sub_off = np.concatenate([[0], np.cumsum(lengths)]).astype(np.int64)
+        sub = torch.empty(int(sub_off[-1]), dtype=torch.float32, device=dev)
+        h.rasterize(cue_start, cue_end, cue_keep, cue_off, self.ratios, K, False, self.sample_rate,
+                    self.start_seconds, out=sub.data_ptr(), out_off=sub_off, memspace=_native.B2_DEVICE)
+        score = torch.empty(B * K, dtype=torch.float64, device=dev)
+        offset = torch.empty(B * K, dtype=torch.int32, device=dev)
+        status = torch.empty(B * K, dtype=torch.int32, device=dev)
+        h.align_batch(ref.data_ptr(), ref_off, sub.data_ptr(), sub_off, B, K, self.max_offset_samples,
+                      score=score.data_ptr(), offset=offset.data_ptr(), status=status.data_ptr(),
+                      memspace=_native.B2_DEVICE)
+        bs = torch.empty(B, dtype=torch.float64, device=dev)
+        bo = torch.empty(B, dtype=torch.int32, device=dev)
+        bk = torch.empty(B, dtype=torch.int32, device=dev)
+        h.reduce_ratios(score.data_ptr(), offset.data_ptr(), status.data_ptr(), B, K, self.max_offset_samples,
+                        best_score=bs.data_ptr(), best_offset=bo.data_ptr(), best_k=bk.data_ptr(),
+                        memspace=_native.B2_DEVICE)
+        h.synchronize()
+        return bs.cpu().numpy(), bo.cpu().numpy(), bk.cpu().numpy()
 
     def sync_host(self, pcm, pcm_off, cue_start, cue_end, cue_off, cue_keep=None, want_all=False):
         """pcm: int16 numpy array (ideally backed by pinned memory).  Blocks until results are on

@@ -394,6 +394,32 @@ extern "C" int b2_rasterize(b2_handle h, const double* cue_start_s, const double
   return B2_OK;
 }
 
+// ---- fused-VAD blend -------------------------------------------------------------------------
+extern "C" int b2_blend_signals(b2_handle h, const float* a, const float* b, int64_t n, int mode,
+                                double wa, double wb, float* out, int memspace) {
+  B2_ENTER(h);
+  if (n < 0 || mode < 0 || mode > 2) B2_FAIL(h, B2_ERR_BAD_ARG, "blend: bad arguments");
+  if (n == 0) return B2_OK;
+  if (!a || !b || !out) B2_FAIL(h, B2_ERR_BAD_ARG, "blend: null pointer");
+  const float *d_a = a, *d_b = b;
+  float* d_out = out;
+  if (memspace == B2_HOST) {
+    void *da, *db, *dq;
+    B2_TRY(stage_in(h, b2_ctx::WS_STAGE_IN0, a, (size_t)n * 4, &da));
+    B2_TRY(stage_in(h, b2_ctx::WS_STAGE_IN1, b, (size_t)n * 4, &db));
+    B2_TRY(b2i_ws(h, b2_ctx::WS_STAGE_OUT, (size_t)n * 4, &dq));
+    d_a = (const float*)da;
+    d_b = (const float*)db;
+    d_out = (float*)dq;
+  }
+  B2_TRY(b2i_blend_launch(h, d_a, d_b, n, mode, wa, wb, d_out));
+  if (memspace == B2_HOST) {
+    B2_TRY(copy_out(h, out, d_out, (size_t)n * 4));
+    B2_CUDA(h, cudaStreamSynchronize(h->stream));
+  }
+  return B2_OK;
+}
+
 // ---- boundaries ----------------------------------------------------------------------------
 extern "C" int b2_first_last_nonzero(b2_handle h, const float* sig, const int64_t* sig_off, int n,
                                      int64_t* first, int64_t* last, int memspace) {

@@ -116,6 +116,8 @@ int b2i_raster_launch(b2_ctx* h, const double* cue_start, const double* cue_end,
                       double start_seconds, float* d_out, const int64_t* out_off_host);
 int b2i_bounds_launch(b2_ctx* h, const float* d_sig, const int64_t* off_host, int n,
                       int64_t* d_first, int64_t* d_last);
+int b2i_blend_launch(b2_ctx* h, const float* d_a, const float* d_b, int64_t n, int mode, double wa,
+                     double wb, float* d_out);
 int b2i_align_launch(b2_ctx* h, const float* d_ref, const int64_t* ref_off_host,
                      const float* d_sub, const int64_t* sub_off_host, int B, int K,
                      int32_t max_offset_samples, double* d_score, int32_t* d_offset,

@@ -128,7 +128,31 @@ __global__ void __launch_bounds__(128) reduce_ratios_kernel(const double* __rest
   best_offset[b] = bo;
 }
 
+// ---- fused-VAD blend (speech_transformers.py:281-294) ----------------------------------------
+__global__ void __launch_bounds__(256) blend_kernel(const float* __restrict__ a,
+                                                     const float* __restrict__ b, long long n,
+                                                     int mode, double wa, double wb,
+                                                     float* __restrict__ out) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n;
+       i += (long long)gridDim.x * blockDim.x) {
+    const float x = a[i], y = b[i];
+    float r;
+    if (mode == 0) r = fminf(x, y);
+    else if (mode == 1) r = fmaxf(x, y);
+    else r = (float)__dadd_rn(__dmul_rn(wa, (double)x), __dmul_rn(wb, (double)y));
+    out[i] = r;
+  }
+}
+
 }  // namespace
+
+int b2i_blend_launch(b2_ctx* h, const float* d_a, const float* d_b, int64_t n, int mode, double wa,
+                     double wb, float* d_out) {
+  int blocks = (int)std::min<int64_t>((n + 255) / 256, (int64_t)h->sm_count * 8);
+  blend_kernel<<<blocks, 256, 0, h->stream>>>(d_a, d_b, n, mode, wa, wb, d_out);
+  B2_CHECK_LAUNCH(h, "blend_kernel");
+  return B2_OK;
+}
 
 int b2i_raster_launch(b2_ctx* h, const double* cue_start, const double* cue_end,
                       const uint8_t* cue_keep, const int64_t* cue_off, int B, const double* ratios,

@@ -84,10 +84,51 @@ def _make_energy_zcr_detector(
     return _detect
 
 
+def _make_energy_detector(sample_rate: int, frame_rate: int, non_speech_label: float):
+    """Energy-only variant (no zero-crossing band): what auditok's energy validator keeps
+    (speech_transformers.py:125) before its tokenizer."""
+    fpw = int((1.0 / sample_rate) * frame_rate + 0.5)
+    return _make_energy_zcr_detector(sample_rate, frame_rate, non_speech_label, z_lo=0, z_hi=fpw)
+
+
 #: name fragment looked up in ``VideoSpeechTransformer.vad`` -> factory(sample_rate, frame_rate, label)
 DETECTOR_FACTORIES: Dict[str, Callable[[int, int, float], Callable]] = {
+    "energy_only": _make_energy_detector,
     "energy": _make_energy_zcr_detector,
 }
+
+_FUSION_STRATEGIES = ("weighted", "intersection", "union")
+_FUSION_MODE = {"intersection": 0, "union": 1, "weighted": 2}
+
+
+def _make_fused_detector(
+    sample_rate: int,
+    frame_rate: int,
+    non_speech_label: float,
+    fusion_strategy: str = "weighted",
+    factories=None,
+) -> Callable[[Union[bytes, np.ndarray]], np.ndarray]:
+    """Combine two detectors like the reference's fused VAD (speech_transformers.py:256-296):
+    clip both outputs to their common length, then ``intersection`` = element-wise min, ``union`` =
+    max, ``weighted`` (default) = 0.6 * first + 0.4 * second (the reference weights silero 0.6 and
+    webrtc 0.4).  The blend runs on the GPU (b2_blend_signals).  ``factories`` = two detector
+    factories with the reference signature; default: the energy/zero-crossing detector (0.6)
+    and its energy-only variant (0.4)."""
+    if fusion_strategy not in _FUSION_STRATEGIES:
+        raise ValueError("unknown fused VAD strategy %r; choose one of %s"
+                         % (fusion_strategy, ", ".join(_FUSION_STRATEGIES)))
+    first_factory, second_factory = factories or (_make_energy_zcr_detector, _make_energy_detector)
+    first = first_factory(sample_rate, frame_rate, non_speech_label)
+    second = second_factory(sample_rate, frame_rate, non_speech_label)
+    mode = _FUSION_MODE[fusion_strategy]
+
+    def _detect(asegment) -> np.ndarray:
+        a, b = np.asarray(first(asegment), dtype=float), np.asarray(second(asegment), dtype=float)
+        if min(len(a), len(b)) == 0:
+            return np.zeros(0)
+        return _native.get_handle().blend_signals(a, b, mode, 0.6, 0.4).astype(np.float64)
+
+    return _detect
 
 
 # ---------------------------------------------------------------------------------- boundaries
@@ -155,6 +196,9 @@ class VideoSpeechTransformer(TransformerMixin):
 
     # -- detector dispatch (speech_transformers.py:655-679) -----------------------------------
     def _make_detector(self):
+        if "fused" in self.vad:  # "fused" or "fused:intersection" ...; default strategy is weighted
+            strategy = self.vad.split(":", 1)[1] if ":" in self.vad else "weighted"
+            return _make_fused_detector(self.sample_rate, self.frame_rate, self._non_speech_label, strategy)
         for key, factory in DETECTOR_FACTORIES.items():
             if key in self.vad:
                 return factory(self.sample_rate, self.frame_rate, self._non_speech_label)

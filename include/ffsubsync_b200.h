@@ -95,6 +95,14 @@ int b2_rasterize(b2_handle h, const double* cue_start_s, const double* cue_end_s
                  const double* levels /* or NULL */, int sample_rate, double start_seconds,
                  float* out, const int64_t* out_off /* [B*K+1] */, int memspace);
 
+/* ---- fused-VAD blend ------------------------------------------------------------------------
+ * ffsubsync/speech_transformers.py:281-294 (_make_fused_detector._detect): two detector outputs
+ * clipped to their common length n and combined element-wise.
+ * mode 0 "intersection" = min(a, b); 1 "union" = max(a, b); 2 "weighted" = wa*a + wb*b computed
+ * in float64 like the reference (0.6 * silero + 0.4 * webrtc there) and rounded once to float32. */
+int b2_blend_signals(b2_handle h, const float* a, const float* b, int64_t n, int mode, double wa,
+                     double wb, float* out, int memspace);
+
 /* ---- ComputeSpeechFrameBoundariesMixin.fit_boundaries -------------------------------------
  * ffsubsync/speech_transformers.py:310-317: first/last index with value > 0.5, or -1/-1. */
 int b2_first_last_nonzero(b2_handle h, const float* sig, const int64_t* sig_off, int n,

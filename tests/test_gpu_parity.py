@@ -99,6 +99,36 @@ def test_device_memspace_is_ordered_on_the_callers_stream(handle):
         handle.set_stream(None)
 
 
+def test_fused_detector_blend_kats(handle):
+    """The reference's tests/test_vad_fused.py:21-54 with stub constituents: min / max / 0.6-0.4
+    blend, default strategy, common-length clip, unknown strategy."""
+    from ffsubsync_b200.speech_transformers import VideoSpeechTransformer, _make_fused_detector
+
+    def stubs(first, second):
+        return (lambda *a: (lambda seg: np.asarray(first, dtype=float)),
+                lambda *a: (lambda seg: np.asarray(second, dtype=float)))
+
+    # the reference weights silero (here: first) 0.6 and webrtc (second) 0.4
+    silero, webrtc = [1.0, 0.0, 0.0], [1.0, 1.0, 0.0]
+    assert list(_make_fused_detector(100, 48000, 0.0, "intersection", stubs(silero, webrtc))(b"")) == [1.0, 0.0, 0.0]
+    assert list(_make_fused_detector(100, 48000, 0.0, "union", stubs(silero, webrtc))(b"")) == [1.0, 1.0, 0.0]
+    assert np.allclose(_make_fused_detector(100, 48000, 0.0, "weighted", stubs([0.0, 1.0], [1.0, 0.0]))(b""), [0.4, 0.6])
+    assert np.allclose(_make_fused_detector(100, 48000, 0.0, factories=stubs([0.0], [1.0]))(b""), [0.4])
+    assert len(_make_fused_detector(100, 48000, 0.0, "union", stubs([1.0, 1.0], [1.0, 1.0, 1.0]))(b"")) == 2
+    with pytest.raises(ValueError, match="unknown fused VAD strategy"):
+        _make_fused_detector(100, 48000, 0.0, "bogus")
+    # real constituents on PCM: energy/ZCR (0.6) + energy-only (0.4); loud hiss passes only the latter
+    cls = np.array([0, 1, 2, 1, 0, 2], dtype=np.uint8)
+    pcm = vo.synth_pcm(cls, 160, seed=8).tobytes()
+    t = VideoSpeechTransformer("fused", 100, 16000, 0.0).fit(pcm)
+    assert np.allclose(t.transform(), [0.0, 1.0, 0.4, 1.0, 0.0, 0.4])
+    assert list(VideoSpeechTransformer("fused:intersection", 100, 16000, 0.0).fit(pcm).transform()) == [0, 1, 0, 1, 0, 0]
+    rng = np.random.RandomState(1)
+    a, b = rng.rand(100003).astype(np.float32), rng.rand(100003).astype(np.float32)
+    got = handle.blend_signals(a, b, 2, 0.6, 0.4)
+    assert np.array_equal(got, (0.6 * a.astype(np.float64) + 0.4 * b.astype(np.float64)).astype(np.float32))
+
+
 def test_synth_pcm_matches_numpy_replay(handle):
     cls = np.random.RandomState(2).randint(0, 3, 500).astype(np.uint8)
     got = handle.synth_pcm(cls, len(cls), 160, seed=77)
@@ -345,6 +375,45 @@ def test_gss_fit(handle, golden, gf):
     assert off == want["offset"] and pipe.ratio == want["ratio"] and _score_ok(score, gf(want["score"]))
 
 
+def test_gss_batched_over_pairs(handle):
+    """Batched --gss: every pair follows exactly the evaluation sequence the reference's scalar
+    search would (oracle: golden_section_trace over rasterise + fft_align), 17 rounds."""
+    from oracle import gss_oracle as go
+    from ffsubsync_b200.gss_batch import gss_align_batch
+    specs = [(41, 200.0, 1.0417, 300), (42, 260.0, 0.96, -450), (43, 180.0, 1.0, 77)]
+    refs, cs, ce, cue_off, ref_off = [], [], [], [0], [0]
+    for seed, dur, true_ratio, delta in specs:
+        st, en = cases.synthetic_cues(seed, dur)
+        mask = ro.rasterize(st, en, None, 100, 0, true_ratio)[0] != 0
+        n = int(dur * 100 * 1.06) + 700
+        ref = np.zeros(n)
+        src = np.arange(n) - delta
+        ok = (src >= 0) & (src < len(mask))
+        ref[ok] = mask[src[ok]]
+        ref = np.where(np.random.RandomState(seed).rand(n) < 0.08, 1 - ref, ref)
+        refs.append(ref)
+        cs.append(st)
+        ce.append(en)
+        cue_off.append(cue_off[-1] + len(st))
+        ref_off.append(ref_off[-1] + n)
+    res = gss_align_batch(np.concatenate(refs).astype(np.float32), ref_off, np.concatenate(cs),
+                          np.concatenate(ce), cue_off, max_offset_samples=6000, handle=handle)
+    assert res.evals.shape == (3, 17)
+    for b, (seed, dur, true_ratio, delta) in enumerate(specs):
+        rec = {}
+
+        def f(ratio, last, b=b):
+            score, off = ao.fft_align(refs[b], ro.rasterize(cs[b], ce[b], None, 100, 0, ratio)[0], 6000)
+            if last:
+                rec.update(score=score, offset=off, ratio=ratio)
+            return -score
+
+        _, calls = go.golden_section_trace(f, 0.9, 1.1)
+        assert [c[0] for c in calls] == res.evals[b].tolist()
+        assert res.ratio[b] == rec["ratio"] and res.offset[b] == rec["offset"]
+        assert _score_ok(res.score[b], rec["score"])
+
+
 # ========================================================================= whole hot path, batch
 
 def _pair(seed, duration_s, ratio_k, delta, grid, fr=16000):
@@ -409,6 +478,40 @@ def test_sync_batch_small_vs_oracle(handle):
             del os.environ["B2_SUBBATCHES"]
         assert np.array_equal(r[0], bs) and np.array_equal(r[1], bo) and np.array_equal(r[2], bk)
         assert np.array_equal(r[3], a_s) and np.array_equal(r[4], a_o)
+
+
+def test_serialized_speech_replay_batch(handle, tmp_path):
+    """make_test_case replay: ref.npz{"speech"} files + cue lists through sync_signals, vs the
+    oracle on the same deserialised signals (DeserializeSpeechTransformer semantics included)."""
+    from ffsubsync_b200.batch import BatchSynchronizer, load_serialized_speech
+    grid = cases.ratio_grid()
+    paths, cs, ce, cue_off, truth = [], [], [], [0], []
+    for i, (seed, dur, k, delta) in enumerate([(51, 150.0, 3, 120), (52, 210.0, 0, -333), (53, 95.0, 6, 5)]):
+        st, en = cases.synthetic_cues(seed, dur)
+        mask = ro.rasterize(st, en, None, 100, 0, grid[k])[0]
+        n = int(dur * 100)
+        ref = np.zeros(n)
+        src = np.arange(n) - delta
+        ok = (src >= 0) & (src < len(mask))
+        ref[ok] = (mask != 0)[src[ok]]
+        ref = np.where(np.random.RandomState(seed).rand(n) < 0.05, 0.3, ref)   # "unsure" frames < 1
+        p = str(tmp_path / ("ref%d.npz" % i))
+        np.savez_compressed(p, speech=ref)
+        paths.append(p)
+        cs.append(st)
+        ce.append(en)
+        cue_off.append(cue_off[-1] + len(st))
+        truth.append((k, delta))
+    sig, off = load_serialized_speech(paths, non_speech_label=0.0)
+    bs = BatchSynchronizer(grid, max_offset_seconds=60)
+    score, offset, best_k = bs.sync_signals(sig, off, np.concatenate(cs), np.concatenate(ce), cue_off)
+    for b in range(3):
+        ref = sig[off[b]:off[b + 1]].astype(np.float64)
+        assert set(np.unique(ref)) <= {0.0, 1.0}          # values < 1 were relabelled
+        subs = [ro.rasterize(cs[b], ce[b], None, 100, 0, r)[0] for r in grid]
+        (ws, wo), wk = ao.max_score_align(ref, subs, 100, 60)
+        assert (best_k[b], offset[b]) == (wk, wo) == truth[b]
+        assert _score_ok(score[b], ws)
 
 
 def test_sync_two_hour_pair_recovers_offset(handle):
