@@ -317,10 +317,10 @@ def cpu_baseline_sample(K, ratios, budget_pairs=None):
     for v in ("OMP_NUM_THREADS", "MKL_NUM_THREADS", "OPENBLAS_NUM_THREADS"):
         os.environ[v] = "1"
     cores = os.cpu_count() or 1
-    # worker processes: measured on the 128-core bench host, 32 workers give 3.3 alignments/s and
+    # worker processes: measured on the 128-core bench host, 16 workers give 4.9 alignments/s, 32 give 3.3 and
     # 128 workers 2.0 (page-fault / memory-bandwidth contention of the numpy path), so more
     # workers do not help the CPU; B2_CPU_WORKERS overrides
-    used = max(1, min(cores, int(os.environ.get("B2_CPU_WORKERS", "32"))))
+    used = max(1, min(cores, int(os.environ.get("B2_CPU_WORKERS", "16"))))
     _cpu_setup(ratios)
     n_pairs = budget_pairs or used
     rate, dt = cpu_pass(n_pairs, used)
@@ -339,10 +339,10 @@ def run_reference(args):
     for v in ("OMP_NUM_THREADS", "MKL_NUM_THREADS", "OPENBLAS_NUM_THREADS"):
         os.environ[v] = "1"
     cores = os.cpu_count() or 1
-    # worker processes: measured on the 128-core bench host, 32 workers give 3.3 alignments/s and
+    # worker processes: measured on the 128-core bench host, 16 workers give 4.9 alignments/s, 32 give 3.3 and
     # 128 workers 2.0 (page-fault / memory-bandwidth contention of the numpy path), so more
     # workers do not help the CPU; B2_CPU_WORKERS overrides
-    used = max(1, min(cores, int(os.environ.get("B2_CPU_WORKERS", "32"))))
+    used = max(1, min(cores, int(os.environ.get("B2_CPU_WORKERS", "16"))))
     _cpu_setup(ratios)
     per_step = used
     for _ in range(min(args.warmup, 1)):   # one warm-up pass is enough for a CPU pool; bounded runtime
