@@ -58,8 +58,37 @@ class ClockSampler:
 
     def __init__(self, index):
         self.index, self.rows, self.proc = index, [], None
+        self.nvml_samples, self.nvml_stop, self.nvml_thread = None, None, None
+
+    def _start_nvml(self):
+        """Poll NVML every ~2 ms from a thread (the timed region can be shorter than one
+        nvidia-smi sampling period)."""
+        import pynvml
+        pynvml.nvmlInit()
+        dev = pynvml.nvmlDeviceGetHandleByIndex(self.index)
+        self.sm_max = pynvml.nvmlDeviceGetMaxClockInfo(dev, pynvml.NVML_CLOCK_SM)
+        self.nvml_samples, self.nvml_stop = [], threading.Event()
+        names = {"hw_slowdown": pynvml.nvmlClocksEventReasonHwSlowdown,
+                 "hw_thermal_slowdown": pynvml.nvmlClocksEventReasonHwThermalSlowdown,
+                 "sw_thermal_slowdown": pynvml.nvmlClocksEventReasonSwThermalSlowdown,
+                 "sw_power_cap": pynvml.nvmlClocksEventReasonSwPowerCap}
+
+        def loop():
+            while not self.nvml_stop.is_set():
+                clk = pynvml.nvmlDeviceGetClockInfo(dev, pynvml.NVML_CLOCK_SM)
+                mask = pynvml.nvmlDeviceGetCurrentClocksEventReasons(dev)
+                self.nvml_samples.append((clk, [n for n, bit in names.items() if mask & bit]))
+                time.sleep(0.002)
+
+        self.nvml_thread = threading.Thread(target=loop, daemon=True)
+        self.nvml_thread.start()
 
     def start(self):
+        try:
+            self._start_nvml()
+            return
+        except Exception:
+            self.nvml_samples = None
         try:
             self.proc = subprocess.Popen(
                 ["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.FIELDS,
@@ -74,6 +103,13 @@ class ClockSampler:
             self.rows.append(line.strip())
 
     def stop(self):
+        if self.nvml_samples is not None:
+            self.nvml_stop.set()
+            self.nvml_thread.join(1.0)
+            clocks = [c for c, _ in self.nvml_samples]
+            reasons = sorted({r for _, rs in self.nvml_samples for r in rs})
+            return {"sm_mhz": float(np.median(clocks)) if clocks else None, "sm_max_mhz": float(self.sm_max),
+                    "samples": len(clocks), "reasons": reasons, "source": "nvml, sampled during the timed region"}
         if self.proc is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         time.sleep(0.15)
