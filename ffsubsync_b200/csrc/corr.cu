@@ -62,8 +62,18 @@ __device__ __forceinline__ void l2_prefetch(const void* p, uint32_t bytes) {
 }
 
 // ------------------------------------------------------------------------------------------
+// Bulk L2 prefetch of [p, p + n floats), trimmed to 16-byte granules inside the range.
+__device__ __forceinline__ void l2_prefetch_floats(const float* p, int n) {
+  if (n <= 0) return;
+  const uintptr_t a0 = (reinterpret_cast<uintptr_t>(p) + 15) & ~uintptr_t(15);
+  const uintptr_t a1 = reinterpret_cast<uintptr_t>(p + n) & ~uintptr_t(15);
+  if (a1 > a0) l2_prefetch(reinterpret_cast<const void*>(a0), (uint32_t)(a1 - a0));
+}
+
+// Persistent over the reference blocks (one CTA per SM): twiddle tables are built once per CTA
+// and the next item's samples are pulled into L2 while the current one is transformed.
 __global__ void __maxnreg__(96)  // leaves registers for a co-resident VAD CTA (see sub_correlate_kernel)
-    ref_spectra_kernel(const float* __restrict__ ref, const SpecItem* __restrict__ items,
+    ref_spectra_kernel(const float* __restrict__ ref, const SpecItem* __restrict__ items, int n_items,
                        float4* __restrict__ spec, float* __restrict__ spec_energy) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   float2* buf = reinterpret_cast<float2*>(smem_raw);
@@ -71,23 +81,31 @@ __global__ void __maxnreg__(96)  // leaves registers for a co-resident VAD CTA (
   float2* fine32 = tw1024 + 1024;
   __shared__ float red[kThreads / 32];
   const int tid = threadIdx.x;
-  const SpecItem it = items[blockIdx.x];
   init_tables(tw1024, fine32, tid);
   __syncthreads();
   const Tables t{tw1024, fine32};
-  BlockSource s;
-  s.src = ref + it.ref_off + it.i0;
-  s.t_lo = it.i0 < 0 ? -it.i0 : 0;
-  s.t_hi = min(it.R - it.i0, kP);
-  float ss = forward_block(buf, t, tid, s);
-  spec_store(buf, t, tid, spec + (size_t)blockIdx.x * kPairs);
-  for (int o = 16; o > 0; o >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o);
-  if ((tid & 31) == 0) red[tid >> 5] = ss;
-  __syncthreads();
-  if (tid == 0) {
-    float e = 0.f;
-    for (int w = 0; w < kThreads / 32; ++w) e += red[w];
-    spec_energy[blockIdx.x] = e;
+  const PairCtx pc = pair_ctx(tid);
+  for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
+    const SpecItem it = items[item];
+    if (tid == 0 && item + (int)gridDim.x < n_items) {
+      const SpecItem nx = items[item + gridDim.x];
+      const int lo = nx.i0 < 0 ? -nx.i0 : 0, hi = min(nx.R - nx.i0, kP);
+      l2_prefetch_floats(ref + nx.ref_off + nx.i0 + lo, hi - lo);
+    }
+    BlockSource s;
+    s.src = ref + it.ref_off + it.i0;
+    s.t_lo = it.i0 < 0 ? -it.i0 : 0;
+    s.t_hi = min(it.R - it.i0, kP);
+    float ss = forward_block(buf, t, tid, s);
+    spec_store(buf, t, pc, tid, spec + (size_t)item * kPairs);
+    for (int o = 16; o > 0; o >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o);
+    if ((tid & 31) == 0) red[tid >> 5] = ss;
+    __syncthreads();  // also: every thread is done reading buf before the next item overwrites it
+    if (tid == 0) {
+      float e = 0.f;
+      for (int w = 0; w < kThreads / 32; ++w) e += red[w];
+      spec_energy[item] = e;
+    }
   }
 }
 
@@ -150,7 +168,7 @@ __device__ __forceinline__ void tmem_wait_st() {
 // updated.  FIRST: nothing accumulated yet, start from zero instead of loading.
 template <bool FIRST>
 __device__ __forceinline__ void accumulate_block_tmem(uint32_t taddr, const float2* buf,
-                                                      const Tables& t, int tid,
+                                                      const Tables& t, const PairCtx& pc, int tid,
                                                       const float4* __restrict__ spec) {
   float4 b0 = __ldg(spec + tid);
   float4 b1 = __ldg(spec + tid + kThreads);
@@ -174,7 +192,7 @@ __device__ __forceinline__ void accumulate_block_tmem(uint32_t taddr, const floa
       b0 = b1;
       if (u + 2 < 16) b1 = __ldg(spec + tid + (u + 2) * kThreads);
       float2 dp, dq;
-      product_terms(buf, t, tid, u, b, dp, dq);
+      product_terms(buf, t, pc, tid, u, b, dp, dq);
       cur[4 * uu + 0] += dp.x;
       cur[4 * uu + 1] += dp.y;
       cur[4 * uu + 2] += dq.x;
@@ -222,6 +240,7 @@ __device__ __forceinline__ void sub_correlate_body(
     taddr = tmem_base_s + (uint32_t)(((warp & 3) * 32) << 16) + (uint32_t)((warp >> 2) * 64);
   }
   const Tables t{tw1024, fine32};
+  const PairCtx pc = pair_ctx(tid);
   SubState st;
   sub_state_clear(st);
   float er = 0.f;
@@ -230,10 +249,7 @@ __device__ __forceinline__ void sub_correlate_body(
     if (tid == 0 && blk + 1 < job.blk_hi) {
       // pull the next block's samples and reference spectrum into L2 while this block computes
       const int jn = j0 + L;
-      const float* nsrc = sub + job.sub_off + jn;
-      const uintptr_t a0 = (reinterpret_cast<uintptr_t>(nsrc) + 15) & ~uintptr_t(15);
-      const uintptr_t a1 = reinterpret_cast<uintptr_t>(nsrc + min(job.S - jn, L)) & ~uintptr_t(15);
-      if (a1 > a0) l2_prefetch(reinterpret_cast<const void*>(a0), (uint32_t)(a1 - a0));
+      l2_prefetch_floats(sub + job.sub_off + jn, min(job.S - jn, L));
       l2_prefetch(spec + (size_t)(job.spec_base + (blk + 1 - job.blk_lo)) * kPairs, kPairs * 16);
     }
     BlockSource s;
@@ -243,10 +259,10 @@ __device__ __forceinline__ void sub_correlate_body(
     st.ss += forward_block(buf, t, tid, s);
     const size_t item = (size_t)(job.spec_base + (blk - job.blk_lo));
     if (TMEM) {
-      if (blk == job.blk_lo) accumulate_block_tmem<true>(taddr, buf, t, tid, spec + item * kPairs);
-      else accumulate_block_tmem<false>(taddr, buf, t, tid, spec + item * kPairs);
+      if (blk == job.blk_lo) accumulate_block_tmem<true>(taddr, buf, t, pc, tid, spec + item * kPairs);
+      else accumulate_block_tmem<false>(taddr, buf, t, pc, tid, spec + item * kPairs);
     } else {
-      sub_accumulate(st, buf, t, tid, spec + item * kPairs);
+      sub_accumulate(st, buf, t, pc, tid, spec + item * kPairs);
     }
     er += spec_energy[item];
     __syncthreads();  // buf is rewritten by the next block's first pass
@@ -264,7 +280,7 @@ __device__ __forceinline__ void sub_correlate_body(
       }
     }
   }
-  sub_retangle_store(st, buf, t, tid);
+  sub_retangle_store(st, buf, t, pc, tid);
   __syncthreads();
   inverse_passes_1(buf, tid);
   __syncthreads();
@@ -650,8 +666,9 @@ int b2i_align_launch(b2_ctx* h, const float* d_ref, const int64_t* ref_off, cons
     const SubJob* d_jobs = (const SubJob*)b2i_meta_put(&a, jobs.data(), jobs.size() * sizeof(SubJob));
     B2_TRY(b2i_meta_commit(&a));
     if (!items.empty()) {
-      ref_spectra_kernel<<<(unsigned)items.size(), kThreads, kSmemBytes, h->stream>>>(
-          d_ref, d_items, spec, spec_energy);
+      const unsigned grid = (unsigned)std::min<size_t>(items.size(), (size_t)h->sm_count);
+      ref_spectra_kernel<<<grid, kThreads, kSmemBytes, h->stream>>>(d_ref, d_items, (int)items.size(),
+                                                                    spec, spec_energy);
       B2_CHECK_LAUNCH(h, "ref_spectra_kernel");
     }
     if (h->acc_in_tmem)

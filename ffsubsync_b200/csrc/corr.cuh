@@ -204,6 +204,36 @@ CORR_HD float2 pass_twiddle(const Tables& t, int j) {
   return t.tw1024[j << 4];                          // span 64
 }
 
+// Swizzled shared-memory index of element q of radix-16 butterfly u, without re-deriving the
+// swizzle per access (r1c profile: ~20 % of the kernel's instructions were index arithmetic).
+// For butterfly u of the pass with element stride 2^S the index is base + q*2^S with
+// base = ((u >> S) << (S+4)) + (u & (2^S-1)); the XOR swizzle then reduces to
+//   S = 10:  swz(base) + q*1024                          (swizzle bits 4..7 come from j only)
+//   S =  6:  reg[q & 3] + q*64,  reg[m] = base ^ ((j>>4)&3) ^ (m<<2)
+//   S =  2:  reg ^ c(q),         reg = (blk<<6) ^ (((blk&3)<<2) | j),  c(q) compile-time
+// (identities checked exhaustively in tests/test_host_cpu.py via the kernel emulation).
+template <int S>
+CORR_HD void pass_addr_init(int u, int (&reg)[4]) {
+  const int j = u & ((1 << S) - 1);
+  const int base = ((u >> S) << (S + 4)) + j;
+  if (S == 10) {
+    reg[0] = swz(base);
+  } else if (S == 6) {
+    const int b0 = base ^ ((j >> 4) & 3);
+#pragma unroll
+    for (int m = 0; m < 4; ++m) reg[m] = b0 ^ (m << 2);
+  } else {
+    const int blk = u >> 2;
+    reg[0] = (blk << 6) ^ (((blk & 3) << 2) | j);
+  }
+}
+template <int S>
+CORR_HD int pass_addr(const int (&reg)[4], int q) {
+  if (S == 10) return reg[0] + (q << 10);
+  if (S == 6) return reg[q & 3] + (q << 6);
+  return reg[0] ^ (((q & 3) << 2) | ((q >> 2) << 4) | (q >> 2));
+}
+
 // One in-place radix-16 DIF pass over shared memory (spans 1024 and 64).
 template <int SUB_LOG2>
 CORR_HD void dif16_pass_smem(float2* buf, const Tables& t, int tid) {
@@ -211,15 +241,16 @@ CORR_HD void dif16_pass_smem(float2* buf, const Tables& t, int tid) {
   for (int rep = 0; rep < 2; ++rep) {
     const int u = tid + rep * kThreads;
     const int j = u & ((1 << SUB_LOG2) - 1);
-    const int base = ((u >> SUB_LOG2) << (SUB_LOG2 + 4)) + j;
+    int reg[4];
+    pass_addr_init<SUB_LOG2>(u, reg);
     float2 v[16];
 #pragma unroll
-    for (int q = 0; q < 16; ++q) v[q] = buf[swz(base + (q << SUB_LOG2))];
+    for (int q = 0; q < 16; ++q) v[q] = buf[pass_addr<SUB_LOG2>(reg, q)];
     bfly16_dif(v, pass_twiddle<SUB_LOG2>(t, j));
 #pragma unroll
     for (int a = 0; a < 4; ++a)
 #pragma unroll
-      for (int b = 0; b < 4; ++b) buf[swz(base + ((a + 4 * b) << SUB_LOG2))] = v[4 * a + b];
+      for (int b = 0; b < 4; ++b) buf[pass_addr<SUB_LOG2>(reg, a + 4 * b)] = v[4 * a + b];
   }
 }
 
@@ -229,15 +260,16 @@ CORR_HD void dit16_pass_smem(float2* buf, const Tables& t, int tid) {
   for (int rep = 0; rep < 2; ++rep) {
     const int u = tid + rep * kThreads;
     const int j = u & ((1 << SUB_LOG2) - 1);
-    const int base = ((u >> SUB_LOG2) << (SUB_LOG2 + 4)) + j;
+    int reg[4];
+    pass_addr_init<SUB_LOG2>(u, reg);
     float2 v[16];
 #pragma unroll
     for (int a = 0; a < 4; ++a)
 #pragma unroll
-      for (int b = 0; b < 4; ++b) v[4 * a + b] = buf[swz(base + ((a + 4 * b) << SUB_LOG2))];
+      for (int b = 0; b < 4; ++b) v[4 * a + b] = buf[pass_addr<SUB_LOG2>(reg, a + 4 * b)];
     bfly16_dit(v, cconj(pass_twiddle<SUB_LOG2>(t, j)));
 #pragma unroll
-    for (int q = 0; q < 16; ++q) buf[swz(base + (q << SUB_LOG2))] = v[q];
+    for (int q = 0; q < 16; ++q) buf[pass_addr<SUB_LOG2>(reg, q)] = v[q];
   }
 }
 
@@ -246,14 +278,14 @@ template <bool INV>
 CORR_HD void r4_pass_smem(float2* buf, int tid) {
 #pragma unroll 2
   for (int rep = 0; rep < kM / 4 / kThreads; ++rep) {
-    const int base = (tid + rep * kThreads) << 2;
-    float2 a0 = buf[swz(base)], a1 = buf[swz(base + 1)], a2 = buf[swz(base + 2)],
-           a3 = buf[swz(base + 3)];
+    // swz(4u + q) = swz(4u) ^ q: q only occupies bits 0..1, which the swizzle XORs but never reads
+    const int s0 = swz((tid + rep * kThreads) << 2);
+    float2 a0 = buf[s0], a1 = buf[s0 ^ 1], a2 = buf[s0 ^ 2], a3 = buf[s0 ^ 3];
     r4<INV>(a0, a1, a2, a3);
-    buf[swz(base)] = a0;
-    buf[swz(base + 1)] = a1;
-    buf[swz(base + 2)] = a2;
-    buf[swz(base + 3)] = a3;
+    buf[s0] = a0;
+    buf[s0 ^ 1] = a1;
+    buf[s0 ^ 2] = a2;
+    buf[s0 ^ 3] = a3;
   }
 }
 
@@ -326,10 +358,11 @@ CORR_HD float dif16_pass1_global(float2* buf, const Tables& t, int tid,
 #pragma unroll
     for (int q = 0; q < 16; ++q) ss += v[q].x * v[q].x + v[q].y * v[q].y;
     bfly16_dif(v, pass_twiddle<10>(t, j));
+    const int s0 = swz(j);  // swz(j + k*1024) = swz(j) + k*1024
 #pragma unroll
     for (int a = 0; a < 4; ++a)
 #pragma unroll
-      for (int b = 0; b < 4; ++b) buf[swz(j + ((a + 4 * b) << 10))] = v[4 * a + b];
+      for (int b = 0; b < 4; ++b) buf[s0 + ((a + 4 * b) << 10)] = v[4 * a + b];
   }
   return ss;
 }
@@ -392,17 +425,45 @@ CORR_HD void slot_positions(int r, int& p, int& q) {
   }
 }
 
-CORR_HD void untangle_slot(const float2* buf, const Tables& t, int r, float2& hp, float2& hq) {
-  if (r >= 2) {
-    const int p = 2 * r;
-    untangle_pair(buf, t, p, partner_pos(p), hp, hq);
-  } else if (r == 0) {
-    const float2 z0 = buf[swz(0)];
-    hp = make_float2(2.f * (z0.x + z0.y), 2.f * (z0.x - z0.y));
-    hq = untangle_one(buf, t, 2);
-  } else {
-    untangle_pair(buf, t, 1, 3, hp, hq);
+// Per-thread constants of that map, computed once per kernel.  For u >= 1 the pair r = tid + 512u
+// has p = 1024u + 2 tid and partner q = 1024(16-u) + (1023 - 2 tid) (the digit-reversed image of
+// f -> M - f when the lowest frequency digit u is non-zero), frequency f = F(tid) | u; the
+// swizzled addresses are then a per-thread base plus a compile-time multiple of 1024.
+struct PairCtx {
+  int sp0;     // swz(2 tid)
+  int sq0;     // swz(1023 - 2 tid)
+  int sq_u0;   // swz(partner of position 2 tid)     (u = 0, tid >= 2)
+  int f_base;  // freq_of_pos(2 tid): low 4 bits are zero
+};
+CORR_HD PairCtx pair_ctx(int tid) {
+  PairCtx c;
+  c.sp0 = swz(2 * tid);
+  c.sq0 = swz(1023 - 2 * tid);
+  c.sq_u0 = swz(partner_pos(2 * tid));
+  c.f_base = freq_of_pos(2 * tid);
+  return c;
+}
+
+// H[p], H[q] of pair slot u of this thread (see untangle_pair for the algebra).
+CORR_HD void untangle_slot(const float2* buf, const Tables& t, const PairCtx& c, int tid, int u,
+                           float2& hp, float2& hq) {
+  if (u == 0 && tid < 2) {
+    if (tid == 0) {
+      const float2 z0 = buf[swz(0)];
+      hp = make_float2(2.f * (z0.x + z0.y), 2.f * (z0.x - z0.y));
+      hq = untangle_one(buf, t, 2);
+    } else {
+      untangle_pair(buf, t, 1, 3, hp, hq);
+    }
+    return;
   }
+  const float2 zp = buf[c.sp0 + (u << 10)];
+  const float2 zq = buf[u == 0 ? c.sq_u0 : c.sq0 + ((16 - u) << 10)];
+  const float2 e = make_float2(zp.x + zq.x, zp.y - zq.y);
+  const float2 d = make_float2(zp.x - zq.x, zp.y + zq.y);
+  const float2 tt = cmul(twiddle15(t, c.f_base | u), d);
+  hp = make_float2(e.x + tt.y, e.y - tt.x);
+  hq = make_float2(e.x - tt.y, -e.y - tt.x);
 }
 
 // Inverse of the packing for the accumulated product spectrum C (position order):
@@ -435,21 +496,20 @@ CORR_HD void sub_state_clear(SubState& st) {
 }
 
 // Producer: packed half spectrum (x2) of the reference block in buf -> spec[kPairs] float4.
-CORR_HD void spec_store(const float2* buf, const Tables& t, int tid, float4* spec) {
-#pragma unroll 4
+CORR_HD void spec_store(const float2* buf, const Tables& t, const PairCtx& c, int tid, float4* spec) {
+#pragma unroll
   for (int u = 0; u < 16; ++u) {
-    const int r = tid + u * kThreads;
     float2 hp, hq;
-    untangle_slot(buf, t, r, hp, hq);
-    spec[r] = make_float4(hp.x, hp.y, hq.x, hq.y);
+    untangle_slot(buf, t, c, tid, u, hp, hq);
+    spec[tid + u * kThreads] = make_float4(hp.x, hp.y, hq.x, hq.y);
   }
 }
 
 // conj(A) * B for the thread's pair slot u: A from the subtitle block spectrum in buf, B = b.
-CORR_HD void product_terms(const float2* buf, const Tables& t, int tid, int u, float4 b, float2& dp,
-                           float2& dq) {
+CORR_HD void product_terms(const float2* buf, const Tables& t, const PairCtx& c, int tid, int u,
+                           float4 b, float2& dp, float2& dq) {
   float2 hp, hq;
-  untangle_slot(buf, t, tid + u * kThreads, hp, hq);
+  untangle_slot(buf, t, c, tid, u, hp, hq);
   if (u == 0 && tid == 0) {
     dp = make_float2(hp.x * b.x, hp.y * b.y);  // two real bins: DC and Nyquist
   } else {
@@ -461,8 +521,8 @@ CORR_HD void product_terms(const float2* buf, const Tables& t, int tid, int u, f
 // Consumer: acc += conj(A) * B for the subtitle block spectrum in buf and the stored B.
 // (Register-accumulator form; the device kernel keeps the accumulators in tensor memory instead,
 // see sub_correlate_kernel - this form is what tests/host_emul runs.)
-CORR_HD void sub_accumulate(SubState& st, const float2* buf, const Tables& t, int tid,
-                            const float4* spec) {
+CORR_HD void sub_accumulate(SubState& st, const float2* buf, const Tables& t, const PairCtx& c,
+                            int tid, const float4* spec) {
   // the stored reference spectrum is read two slots ahead of its use (L2 latency)
   float4 b0 = CORR_LDG(spec + tid);
   float4 b1 = CORR_LDG(spec + tid + kThreads);
@@ -473,7 +533,7 @@ CORR_HD void sub_accumulate(SubState& st, const float2* buf, const Tables& t, in
     b0 = b1;
     if (u + 2 < 16) b1 = CORR_LDG(spec + r + 2 * kThreads);
     float2 dp, dq;
-    product_terms(buf, t, tid, u, b, dp, dq);
+    product_terms(buf, t, c, tid, u, b, dp, dq);
     st.cp[u] = cadd(st.cp[u], dp);
     st.cq[u] = cadd(st.cq[u], dq);
   }
@@ -481,10 +541,10 @@ CORR_HD void sub_accumulate(SubState& st, const float2* buf, const Tables& t, in
 
 // Consumer, after the last block: accumulated spectrum -> position-order input of the inverse
 // transform, written into buf (every position is written exactly once).
-CORR_HD void sub_retangle_store(const SubState& st, float2* buf, const Tables& t, int tid) {
+CORR_HD void sub_retangle_store(const SubState& st, float2* buf, const Tables& t, const PairCtx& c,
+                                int tid) {
 #pragma unroll
   for (int u = 0; u < 16; ++u) {
-    const int r = tid + u * kThreads;
     float2 zp, zq;
     if (u == 0 && tid == 0) {
       const float c0 = st.cp[0].x, cm = st.cp[0].y;
@@ -493,12 +553,18 @@ CORR_HD void sub_retangle_store(const SubState& st, float2* buf, const Tables& t
       retangle_pair(t, 2, st.cq[0], st.cq[0], zq, unused);
       buf[swz(0)] = zp;
       buf[swz(2)] = zq;
+    } else if (u == 0 && tid == 1) {
+      retangle_pair(t, 1, st.cp[0], st.cq[0], zp, zq);
+      buf[swz(1)] = zp;
+      buf[swz(3)] = zq;
     } else {
-      int p, q;
-      slot_positions(r, p, q);
-      retangle_pair(t, p, st.cp[u], st.cq[u], zp, zq);
-      buf[swz(p)] = zp;
-      buf[swz(q)] = zq;
+      // same algebra as retangle_pair with the thread's precomputed addresses / frequency
+      const float2 cp = st.cp[u], cq = st.cq[u];
+      const float2 e = make_float2(cp.x + cq.x, cp.y - cq.y);
+      const float2 d = make_float2(cp.x - cq.x, cp.y + cq.y);
+      const float2 tt = cmul(cconj(twiddle15(t, c.f_base | u)), d);
+      buf[c.sp0 + (u << 10)] = make_float2(e.x - tt.y, e.y + tt.x);
+      buf[u == 0 ? c.sq_u0 : c.sq0 + ((16 - u) << 10)] = make_float2(e.x + tt.y, -e.y + tt.x);
     }
   }
 }

@@ -50,15 +50,15 @@ int main(int argc, char** argv) {
     rs.t_lo = i0 < 0 ? -i0 : 0;
     rs.t_hi = (R - i0) < kP ? (R - i0) : kP;
     forward_all(buf.data(), t, rs, ss_ref.data());
-    for (int tid = 0; tid < kThreads; ++tid) spec_store(buf.data(), t, tid, spec.data());
+    for (int tid = 0; tid < kThreads; ++tid) spec_store(buf.data(), t, pair_ctx(tid), tid, spec.data());
     BlockSource bs;
     bs.src = sub.data() + j0;
     bs.t_lo = 0;
     bs.t_hi = (S - j0) < L ? (S - j0) : L;
     forward_all(buf.data(), t, bs, ss_sub.data());
-    for (int tid = 0; tid < kThreads; ++tid) sub_accumulate(st[tid], buf.data(), t, tid, spec.data());
+    for (int tid = 0; tid < kThreads; ++tid) sub_accumulate(st[tid], buf.data(), t, pair_ctx(tid), tid, spec.data());
   }
-  for (int tid = 0; tid < kThreads; ++tid) sub_retangle_store(st[tid], buf.data(), t, tid);
+  for (int tid = 0; tid < kThreads; ++tid) sub_retangle_store(st[tid], buf.data(), t, pair_ctx(tid), tid);
   for (int tid = 0; tid < kThreads; ++tid) inverse_passes_1(buf.data(), tid);
   for (int tid = 0; tid < kThreads; ++tid) inverse_passes_2(buf.data(), t, tid);
   for (int tid = 0; tid < kThreads; ++tid) inverse_passes_3(buf.data(), t, tid);
