@@ -332,6 +332,7 @@ int b2i_vad_launch(b2_ctx* h, const int16_t* d_pcm, const int64_t* pcm_off, int 
   p.fpw = fpw;
   p.stage_bytes = ((p.tw * fpw * 2 + 32) + 127) & ~127;
   int stages = kMaxStages;
+  if (const char* e = getenv("B2_VAD_STAGES")) stages = std::max(2, std::min(kMaxStages, atoi(e)));  // tuning knob
   while (stages > 2 && (size_t)stages * p.stage_bytes > 200 * 1024) --stages;
   p.stages = stages;
   size_t smem = (size_t)stages * p.stage_bytes + 2 * kMaxStages * sizeof(uint64_t) +
