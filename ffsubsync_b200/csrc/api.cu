@@ -472,7 +472,7 @@ extern "C" int b2_align_batch(b2_handle h, const float* ref, const int64_t* ref_
     d_status = d_offset + J;
   }
   B2_TRY(b2i_align_launch(h, d_ref, ref_off, d_sub, sub_off, B, K, max_offset_samples, d_score,
-                          d_offset, d_status, /*winner_only=*/0));
+                          d_offset, d_status, /*winner_only=*/0, /*cue_src=*/nullptr));
   if (memspace == B2_HOST) {
     B2_TRY(copy_out(h, score, d_score, J * 8));
     B2_TRY(copy_out(h, offset, d_offset, J * 4));
@@ -557,9 +557,19 @@ extern "C" int b2_sync_batch(b2_handle h, const int16_t* pcm, const int64_t* pcm
   sub_off[0] = 0;
   for (size_t j = 0; j < J; ++j) sub_off[j + 1] = sub_off[j] + lengths[j];
 
-  void *d_refsig, *d_subsig, *d_res;
+  // Fused mode (default): the K subtitle signals of a pair are never materialised - the
+  // correlation kernel rasterises each block from the cue list in shared memory (B2CueSource).
+  // Fallback (B2_FUSED_RASTER=0, or a pair with more cues than the kernel's shared-memory table):
+  // raster_cues_kernel writes float signals to HBM and the generic aligner reads them back.
+  bool fused = true;
+  if (const char* e = getenv("B2_FUSED_RASTER")) fused = atoi(e) != 0;
+  for (int b = 0; b < B && fused; ++b)
+    if (cue_off[b + 1] - cue_off[b] > kB2MaxCuesFused) fused = false;
+  B2CueSource cue_src{cue_start_s, cue_end_s, cue_keep, cue_off, ratios, sample_rate, start_seconds};
+
+  void *d_refsig, *d_subsig = nullptr, *d_res;
   B2_TRY(b2i_ws(h, b2_ctx::WS_SIG_REF, (size_t)ref_off[B] * 4 + 64, &d_refsig));
-  B2_TRY(b2i_ws(h, b2_ctx::WS_SIG_SUB, (size_t)sub_off[J] * 4 + 64, &d_subsig));
+  if (!fused) B2_TRY(b2i_ws(h, b2_ctx::WS_SIG_SUB, (size_t)sub_off[J] * 4 + 64, &d_subsig));
   B2_TRY(b2i_ws(h, b2_ctx::WS_MISC, J * 16 + (size_t)B * 16 + 256, &d_res));
   double* d_score = (double*)d_res;
   double* d_bs = d_score + J;
@@ -613,11 +623,12 @@ extern "C" int b2_sync_batch(b2_handle h, const int16_t* pcm, const int64_t* pcm
       if (st != B2_OK) return st;
     }
     if (n_sub == 1) {
-      B2_TRY(b2i_raster_launch(h, cue_start_s, cue_end_s, cue_keep, cue_off, B, ratios, K, 0, nullptr,
-                               sample_rate, start_seconds, (float*)d_subsig, sub_off.data()));
+      if (!fused)
+        B2_TRY(b2i_raster_launch(h, cue_start_s, cue_end_s, cue_keep, cue_off, B, ratios, K, 0, nullptr,
+                                 sample_rate, start_seconds, (float*)d_subsig, sub_off.data()));
       B2_TRY(b2i_align_launch(h, (const float*)d_refsig, ref_off.data(), (const float*)d_subsig,
                               sub_off.data(), B, K, max_offset_samples, o_score, o_offset, d_status,
-                              winner_only));
+                              winner_only, fused ? &cue_src : nullptr));
       B2_TRY(b2i_reduce_launch(h, o_score, o_offset, d_status, B, K, max_offset_samples, o_bs, o_bo,
                                o_bk));
       break;
@@ -628,12 +639,15 @@ extern "C" int b2_sync_batch(b2_handle h, const int16_t* pcm, const int64_t* pcm
       Stream2Scope on2(h);
       B2_CUDA(h, cudaStreamWaitEvent(h->stream, vad_done, 0));
       const size_t j0 = (size_t)b0 * K;
-      B2_TRY(b2i_raster_launch(h, cue_start_s, cue_end_s, cue_keep, cue_off + b0, nb, ratios, K, 0,
-                               nullptr, sample_rate, start_seconds, (float*)d_subsig,
-                               sub_off.data() + j0));
+      if (!fused)
+        B2_TRY(b2i_raster_launch(h, cue_start_s, cue_end_s, cue_keep, cue_off + b0, nb, ratios, K, 0,
+                                 nullptr, sample_rate, start_seconds, (float*)d_subsig,
+                                 sub_off.data() + j0));
+      B2CueSource sub_src = cue_src;
+      sub_src.cue_off = cue_off + b0;
       B2_TRY(b2i_align_launch(h, (const float*)d_refsig, ref_off.data() + b0, (const float*)d_subsig,
                               sub_off.data() + j0, nb, K, max_offset_samples, o_score + j0,
-                              o_offset + j0, d_status + j0, winner_only));
+                              o_offset + j0, d_status + j0, winner_only, fused ? &sub_src : nullptr));
       B2_TRY(b2i_reduce_launch(h, o_score + j0, o_offset + j0, d_status + j0, nb, K,
                                max_offset_samples, o_bs + b0, o_bo + b0, o_bk + b0));
       done2 = next_event(h);

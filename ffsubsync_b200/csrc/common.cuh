@@ -118,10 +118,22 @@ int b2i_bounds_launch(b2_ctx* h, const float* d_sig, const int64_t* off_host, in
                       int64_t* d_first, int64_t* d_last);
 int b2i_blend_launch(b2_ctx* h, const float* d_a, const float* d_b, int64_t n, int mode, double wa,
                      double wb, float* d_out);
+// Cue mode of the aligner (b2_sync_batch): subtitle signals are rasterised from the cue list
+// inside the correlation kernel; all arrays are HOST pointers, cue_off has B+1 absolute entries.
+struct B2CueSource {
+  const double* cue_start;
+  const double* cue_end;
+  const uint8_t* cue_keep;   // may be null
+  const int64_t* cue_off;
+  const double* ratios;      // [K]
+  int sample_rate;
+  double start_seconds;
+};
+constexpr int kB2MaxCuesFused = 4096;  // per pair (shared-memory budget of the cue-mode kernel)
 int b2i_align_launch(b2_ctx* h, const float* d_ref, const int64_t* ref_off_host,
                      const float* d_sub, const int64_t* sub_off_host, int B, int K,
                      int32_t max_offset_samples, double* d_score, int32_t* d_offset,
-                     int32_t* d_status, int winner_only);
+                     int32_t* d_status, int winner_only, const B2CueSource* cue_src);
 int b2i_reduce_launch(b2_ctx* h, const double* d_score, const int32_t* d_offset,
                       const int32_t* d_status, int B, int K, int32_t max_offset_samples,
                       double* d_best_score, int32_t* d_best_offset, int32_t* d_best_k);

@@ -22,6 +22,7 @@
 
 #include "common.cuh"
 #include "corr.cuh"
+#include "raster_math.cuh"
 
 namespace {
 
@@ -44,6 +45,12 @@ struct SubJob {        // one (pair, ratio, offset tile)
   long long score_off; // where the tile's Wt scores go
   long long spec_base; // index of the spectrum of block blk_lo
   int S, blk_lo, blk_hi, n_out, energy_slot;
+  // rasterise-on-the-fly mode (subtitle signal generated from the cue list inside the kernel)
+  long long cue_lo;    // first cue of the pair in the uploaded cue arrays
+  long long bits_off;  // word offset of this (pair, ratio)'s speech bit mask (side output)
+  double ratio;
+  int n_cues;
+  float hi;            // 2*min(1/ratio, 1) - 1: value of a frame inside a cue after x -> 2x-1
 };
 
 struct SelJob {        // one (pair, ratio)
@@ -54,7 +61,20 @@ struct SelJob {        // one (pair, ratio)
   int out_index;       // b*K + k
   int kind;            // 0 normal, 1 empty input, 2 everything masked
   int masked_offset;   // offset reported when kind == 2
+  long long bits_off;  // >= 0: the subtitle signal is the bit mask written by the cue-mode kernel
+  float sub_level;     // value of a frame inside a cue, min(1/ratio, 1) as float32 (cue mode)
 };
+
+struct CueArrays {     // device copies of the batch's cue list (cue-mode only)
+  const double* start_s;
+  const double* end_s;
+  const unsigned char* keep;  // may be null
+  double start_seconds;
+  int sample_rate;
+};
+
+constexpr int kMaxCuesFused = 4096;  // per pair; more -> the caller uses the rasterise-to-HBM path
+constexpr size_t kSmemBytesCues = kSmemBytes + (size_t)kP + (size_t)kMaxCuesFused * 8;
 
 // Bulk L2 prefetch (16-byte aligned address, size a multiple of 16).
 __device__ __forceinline__ void l2_prefetch(const void* p, uint32_t bytes) {
@@ -208,15 +228,23 @@ __device__ __forceinline__ void accumulate_block_tmem(uint32_t taddr, const floa
   tmem_wait_st();
 }
 
-template <bool TMEM>
+// CUES = false: the subtitle signal is a float array in global memory (b2_align_batch).
+// CUES = true : it is generated block by block from the pair's cue list (b2_sync_batch): the
+//   scaled cue bounds are computed once per CTA (bit-exact reference arithmetic, raster_math.cuh),
+//   each block's frames are rasterised into a byte mask in shared memory, the first FFT pass
+//   reads that mask, and the mask is also written out as a bit mask (1/32 of the float signal)
+//   for the exact re-score.  No subtitle signal ever exists in HBM.
+template <bool TMEM, bool CUES>
 __device__ __forceinline__ void sub_correlate_body(
     const float* __restrict__ sub, const SubJob* __restrict__ jobs, const float4* __restrict__ spec,
     const float* __restrict__ spec_energy, int L, float* __restrict__ scores,
-    float2* __restrict__ job_energy) {
+    float2* __restrict__ job_energy, CueArrays cues, uint32_t* __restrict__ sub_bits) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   float2* buf = reinterpret_cast<float2*>(smem_raw);
   float2* tw1024 = buf + kM;
   float2* fine32 = tw1024 + 1024;
+  unsigned char* mask = smem_raw + kSmemBytes;                   // kP bytes      (CUES only)
+  int2* cue_bounds = reinterpret_cast<int2*>(mask + kP);         // kMaxCuesFused (CUES only)
   __shared__ float red[kThreads / 32];
   __shared__ uint32_t tmem_base_s;
   const int tid = threadIdx.x;
@@ -228,6 +256,16 @@ __device__ __forceinline__ void sub_correlate_body(
     return;
   }
   init_tables(tw1024, fine32, tid);
+  if (CUES) {
+    for (int c = tid; c < job.n_cues; c += kThreads) {
+      const long long gc = job.cue_lo + c;
+      long long first = 0, last = 0;
+      if (!cues.keep || cues.keep[gc])
+        b2_cue_bounds(cues.start_s[gc], cues.end_s[gc], job.ratio, cues.start_seconds,
+                      cues.sample_rate, (long long)job.S, first, last);
+      cue_bounds[c] = make_int2((int)first, (int)last);
+    }
+  }
   uint32_t taddr = 0;
   if (TMEM) {
     if (tid < 32) tmem_alloc(&tmem_base_s);
@@ -249,14 +287,45 @@ __device__ __forceinline__ void sub_correlate_body(
     if (tid == 0 && blk + 1 < job.blk_hi) {
       // pull the next block's samples and reference spectrum into L2 while this block computes
       const int jn = j0 + L;
-      l2_prefetch_floats(sub + job.sub_off + jn, min(job.S - jn, L));
+      if (!CUES) l2_prefetch_floats(sub + job.sub_off + jn, min(job.S - jn, L));
       l2_prefetch(spec + (size_t)(job.spec_base + (blk + 1 - job.blk_lo)) * kPairs, kPairs * 16);
     }
-    BlockSource s;
-    s.src = sub + job.sub_off + j0;
-    s.t_lo = 0;
-    s.t_hi = min(job.S - j0, L);
-    st.ss += forward_block(buf, t, tid, s);
+    if (CUES) {
+      // rasterise frames [j0, j0 + L) of this (pair, ratio) into the byte mask
+      for (int i = tid; i < (L >> 4); i += kThreads) reinterpret_cast<uint4*>(mask)[i] = make_uint4(0, 0, 0, 0);
+      __syncthreads();
+      const int lane = tid & 31;
+      for (int c = tid >> 5; c < job.n_cues; c += kThreads / 32) {
+        const int2 bd = cue_bounds[c];
+        const int lo = max(bd.x, j0) - j0, hi = min(bd.y, j0 + L) - j0;
+        for (int i = lo + lane; i < hi; i += 32) mask[i] = 1;
+      }
+      __syncthreads();
+      for (int wi = tid; wi < (L >> 5); wi += kThreads) {  // side output: 32 frames -> one mask word
+        const uint4* m4 = reinterpret_cast<const uint4*>(mask + 32 * wi);
+        const uint4 a = m4[0], b = m4[1];
+        const uint32_t w[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+        uint32_t bits = 0;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {  // bytes are 0 or 1: gather bit 0 of the 4 bytes of w[k]
+          const uint32_t nib = (w[k] & 1u) | ((w[k] >> 7) & 2u) | ((w[k] >> 14) & 4u) | ((w[k] >> 21) & 8u);
+          bits |= nib << (4 * k);
+        }
+        sub_bits[job.bits_off + (long long)blk * (L >> 5) + wi] = bits;
+      }
+      MaskSource s;
+      s.mask = mask;
+      s.len = L;
+      s.t_hi = min(job.S - j0, L);
+      s.hi = job.hi;
+      st.ss += forward_block(buf, t, tid, s);
+    } else {
+      BlockSource s;
+      s.src = sub + job.sub_off + j0;
+      s.t_lo = 0;
+      s.t_hi = min(job.S - j0, L);
+      st.ss += forward_block(buf, t, tid, s);
+    }
     const size_t item = (size_t)(job.spec_base + (blk - job.blk_lo));
     if (TMEM) {
       if (blk == job.blk_lo) accumulate_block_tmem<true>(taddr, buf, t, pc, tid, spec + item * kPairs);
@@ -315,7 +384,19 @@ __global__ void __maxnreg__(kSubRegs)
     sub_correlate_kernel(const float* __restrict__ sub, const SubJob* __restrict__ jobs,
                          const float4* __restrict__ spec, const float* __restrict__ spec_energy,
                          int L, float* __restrict__ scores, float2* __restrict__ job_energy) {
-  sub_correlate_body<true>(sub, jobs, spec, spec_energy, L, scores, job_energy);
+  sub_correlate_body<true, false>(sub, jobs, spec, spec_energy, L, scores, job_energy, CueArrays{},
+                                  nullptr);
+}
+
+// b2_sync_batch: subtitle blocks rasterised from the cue list inside the kernel (no subtitle
+// signal in HBM); writes the speech bit mask for the exact re-score.
+__global__ void __maxnreg__(kSubRegs)
+    sub_correlate_cues_kernel(const SubJob* __restrict__ jobs, const float4* __restrict__ spec,
+                              const float* __restrict__ spec_energy, int L,
+                              float* __restrict__ scores, float2* __restrict__ job_energy,
+                              CueArrays cues, uint32_t* __restrict__ sub_bits) {
+  sub_correlate_body<true, true>(nullptr, jobs, spec, spec_energy, L, scores, job_energy, cues,
+                                 sub_bits);
 }
 
 // A/B variant (B2_ACC=reg): accumulators in registers, 128 registers per thread.
@@ -324,7 +405,8 @@ __global__ void __launch_bounds__(kThreads, 1)
                                 const float4* __restrict__ spec,
                                 const float* __restrict__ spec_energy, int L,
                                 float* __restrict__ scores, float2* __restrict__ job_energy) {
-  sub_correlate_body<false>(sub, jobs, spec, spec_energy, L, scores, job_energy);
+  sub_correlate_body<false, false>(sub, jobs, spec, spec_energy, L, scores, job_energy, CueArrays{},
+                                   nullptr);
 }
 
 // ---- candidate selection ---------------------------------------------------------------------
@@ -439,6 +521,7 @@ __global__ void __launch_bounds__(256) rescore_kernel(const SelJob* __restrict__
                                                        const int* __restrict__ cand_off,
                                                        const int* __restrict__ work_list,
                                                        const int* __restrict__ work_count,
+                                                       const uint32_t* __restrict__ sub_bits,
                                                        double* __restrict__ cand_partial) {
   __shared__ double sh[256];
   const int total = *work_count * kRescoreSeg;
@@ -455,6 +538,17 @@ __global__ void __launch_bounds__(256) rescore_kernel(const SelJob* __restrict__
     const int a0 = j_lo + seg * per, a1 = min(j_hi, a0 + per);
     double acc = 0.0;
     int i = a0 + threadIdx.x;
+    if (job.bits_off >= 0) {
+      // cue mode: subtitle frame i is bit i of the mask written by sub_correlate_cues_kernel;
+      // its value after x -> 2x-1 is (2*level - 1) inside a cue and -1 outside
+      const uint32_t* bits = sub_bits + job.bits_off;
+      const double hi = 2.0 * (double)job.sub_level - 1.0;
+      for (; i < a1; i += 256) {
+        const double a = ((__ldg(bits + (i >> 5)) >> (i & 31)) & 1u) ? hi : -1.0;
+        const double b = 2.0 * (double)__ldg(r + i + o) - 1.0;
+        acc = fma(a, b, acc);
+      }
+    }
     for (; i + 3 * 256 < a1; i += 4 * 256) {  // 8 independent loads in flight per thread
       float sv[4], rv[4];
 #pragma unroll
@@ -548,8 +642,20 @@ long long floor_div(long long a, long long b) {
 
 int b2i_align_launch(b2_ctx* h, const float* d_ref, const int64_t* ref_off, const float* d_sub,
                      const int64_t* sub_off, int B, int K, int32_t max_offset_samples,
-                     double* d_score, int32_t* d_offset, int32_t* d_status, int winner_only) {
+                     double* d_score, int32_t* d_offset, int32_t* d_status, int winner_only,
+                     const B2CueSource* cue_src) {
   const size_t J = (size_t)B * K;
+  // cue mode: subtitle signals are rasterised inside the correlation kernel from the cue list
+  // (sub_off then only carries the signal lengths); bit masks of the signals are its side output
+  const bool cue_mode = cue_src != nullptr;
+  std::vector<long long> bits_off(cue_mode ? J + 1 : 1, 0);
+  if (cue_mode) {
+    for (int b = 0; b < B; ++b)
+      if (cue_src->cue_off[b + 1] - cue_src->cue_off[b] > kMaxCuesFused)
+        B2_FAIL(h, B2_ERR_UNSUPPORTED, "align: more than %d cues in pair %d (cue mode)", kMaxCuesFused, b);
+    for (size_t j = 0; j < J; ++j)
+      bits_off[j + 1] = bits_off[j] + ((sub_off[j + 1] - sub_off[j]) + kP) / 32 + 1;
+  }
   std::vector<SelJob> sel(J);
   struct PairPlan { long long o_min, o_max; int n_tiles; bool any; };
   std::vector<PairPlan> pp(B);
@@ -572,6 +678,8 @@ int b2i_align_launch(b2_ctx* h, const float* d_ref, const int64_t* ref_off, cons
       s.R = (int)R;
       s.S = (int)S;
       s.out_index = (int)j;
+      s.bits_off = cue_mode ? bits_off[j] : -1;
+      s.sub_level = cue_mode ? (float)std::min(1.0 / cue_src->ratios[k], 1.0) : 0.f;  // speech_transformers.py:977
       if (R == 0 || S == 0) {  // aligners.py:58-66
         s.kind = 1;
         continue;
@@ -604,8 +712,31 @@ int b2i_align_launch(b2_ctx* h, const float* d_ref, const int64_t* ref_off, cons
     }
     if (p.any) max_w = std::max(max_w, p.o_max - p.o_min + 1);
   }
-  const int Wt = (int)(max_w <= kP / 2 + 1 ? (max_w | 1) : (kP / 2 + 1));
+  // offsets per tile: Wt = 1 (mod 32) so that L = P - Wt + 1 is a multiple of 32 (vector loads,
+  // whole words of the speech bit mask per block), at most P/2 + 1
+  const int Wt = (int)(max_w <= kP / 2 + 1 ? 32 * ((max_w + 30) / 32) + 1 : (kP / 2 + 1));
   const int L = kP - Wt + 1;
+  // cue mode: device copies of the cue list + the bit-mask side output
+  CueArrays cue_arrays{};
+  uint32_t* d_bits = nullptr;
+  if (cue_mode) {
+    const size_t c0 = (size_t)cue_src->cue_off[0], nc = (size_t)cue_src->cue_off[B] - c0;
+    MetaArena ca;
+    B2_TRY(b2i_meta_begin(h, &ca, nc * 17 + 1024));
+    cue_arrays.start_s = (const double*)b2i_meta_put(&ca, cue_src->cue_start + c0, nc * 8) - c0;
+    cue_arrays.end_s = (const double*)b2i_meta_put(&ca, cue_src->cue_end + c0, nc * 8) - c0;
+    cue_arrays.keep = cue_src->cue_keep
+                          ? (const unsigned char*)b2i_meta_put(&ca, cue_src->cue_keep + c0, nc) - c0
+                          : nullptr;
+    cue_arrays.start_seconds = cue_src->start_seconds;
+    cue_arrays.sample_rate = cue_src->sample_rate;
+    B2_TRY(b2i_meta_commit(&ca));
+    void* db;
+    B2_TRY(b2i_ws(h, b2_ctx::WS_SIG_SUB, (size_t)bits_off[J] * 4 + 64, &db));
+    d_bits = (uint32_t*)db;
+    B2_CUDA(h, cudaFuncSetAttribute(sub_correlate_cues_kernel,
+                                    cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytesCues));
+  }
 
   // score buffers + per-(pair,ratio) bookkeeping
   long long score_total = 0, energy_total = 0;
@@ -671,7 +802,10 @@ int b2i_align_launch(b2_ctx* h, const float* d_ref, const int64_t* ref_off, cons
                                                                     spec, spec_energy);
       B2_CHECK_LAUNCH(h, "ref_spectra_kernel");
     }
-    if (h->acc_in_tmem)
+    if (cue_mode)
+      sub_correlate_cues_kernel<<<(unsigned)jobs.size(), kThreads, kSmemBytesCues, h->stream>>>(
+          d_jobs, spec, spec_energy, L, scores, job_energy, cue_arrays, d_bits);
+    else if (h->acc_in_tmem)
       sub_correlate_kernel<<<(unsigned)jobs.size(), kThreads, kSmemBytes, h->stream>>>(
           d_sub, d_jobs, spec, spec_energy, L, scores, job_energy);
     else
@@ -718,6 +852,18 @@ int b2i_align_launch(b2_ctx* h, const float* d_ref, const int64_t* ref_off, cons
         jb.blk_hi = (int)std::min<long long>(blk_hi, ceil_div64(s.S, L));
         jb.n_out = Wt;
         jb.energy_slot = s.energy_slot + tile;
+        jb.cue_lo = 0;
+        jb.bits_off = 0;
+        jb.ratio = 1.0;
+        jb.n_cues = 0;
+        jb.hi = 0.f;
+        if (cue_mode) {
+          jb.cue_lo = cue_src->cue_off[b];
+          jb.n_cues = (int)(cue_src->cue_off[b + 1] - cue_src->cue_off[b]);
+          jb.ratio = cue_src->ratios[k];
+          jb.bits_off = s.bits_off;
+          jb.hi = 2.f * s.sub_level - 1.f;  // the value load_block16 gives the float signal
+        }
         jobs.push_back(jb);
       }
     }
@@ -735,8 +881,8 @@ int b2i_align_launch(b2_ctx* h, const float* d_ref, const int64_t* ref_off, cons
   select_candidates_kernel<<<(unsigned)J, 256, 0, h->stream>>>(d_sel, scores, job_stat, K, winner_only,
                                                                 cand_off, cand_cnt, work_list, work_count);
   B2_CHECK_LAUNCH(h, "select_candidates_kernel");
-  rescore_kernel<<<(unsigned)(h->sm_count * 8), 256, 0, h->stream>>>(d_sel, d_ref, d_sub, cand_off,
-                                                                      work_list, work_count, cand_partial);
+  rescore_kernel<<<(unsigned)(h->sm_count * 8), 256, 0, h->stream>>>(
+      d_sel, d_ref, d_sub, cand_off, work_list, work_count, d_bits, cand_partial);
   B2_CHECK_LAUNCH(h, "rescore_kernel");
   pick_kernel<<<(unsigned)((J + 127) / 128), 128, 0, h->stream>>>(d_sel, (int)J, cand_off, cand_cnt,
                                                                    cand_partial, job_stat, d_score,

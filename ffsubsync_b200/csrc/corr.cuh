@@ -345,10 +345,29 @@ CORR_HD void load_block16(const BlockSource& s, int j, float2 (&v)[16]) {
   }
 }
 
-// First DIF pass (span 16384) reading the block straight from global memory.
+// A subtitle block rasterised into shared memory as one byte per 10 ms frame (1 = inside a cue):
+// value(t) = (mask[t] ? hi : -1) for t < t_hi, else 0;  hi = 2*min(1/ratio, 1) - 1.
+struct MaskSource {
+  const unsigned char* mask;  // len bytes (len even)
+  int len, t_hi;
+  float hi;
+};
+CORR_HD void load_block16(const MaskSource& s, int j, float2 (&v)[16]) {
+#pragma unroll
+  for (int q = 0; q < 16; ++q) {
+    const int t0 = 2 * (j + (q << 10));
+    const int tc = min(t0, s.len - 2);
+    const unsigned short m = *reinterpret_cast<const unsigned short*>(s.mask + tc);
+    v[q].x = t0 < s.t_hi ? ((m & 0xff) ? s.hi : -1.f) : 0.f;
+    v[q].y = t0 + 1 < s.t_hi ? ((m >> 8) ? s.hi : -1.f) : 0.f;
+  }
+}
+
+// First DIF pass (span 16384) reading the block straight from its source (global memory for
+// float signals, the shared-memory cue mask for rasterise-on-the-fly).
 // Returns the thread's partial sum of squares of the (transformed) samples it loaded.
-CORR_HD float dif16_pass1_global(float2* buf, const Tables& t, int tid,
-                                                    const BlockSource& s) {
+template <class Source>
+CORR_HD float dif16_pass1_global(float2* buf, const Tables& t, int tid, const Source& s) {
   float ss = 0.f;
 #pragma unroll 1
   for (int rep = 0; rep < 2; ++rep) {
@@ -370,8 +389,8 @@ CORR_HD float dif16_pass1_global(float2* buf, const Tables& t, int tid,
 // Forward transform of one real block: on return (after the trailing __syncthreads) buf holds
 // DFT_M of z[n] = x[2n] + i x[2n+1] in position order.  The caller must have synchronised all
 // readers of buf before calling.
-CORR_HD float forward_block(float2* buf, const Tables& t, int tid,
-                                               const BlockSource& s) {
+template <class Source>
+CORR_HD float forward_block(float2* buf, const Tables& t, int tid, const Source& s) {
   const float ss = dif16_pass1_global(buf, t, tid, s);
   CORR_SYNC();
   dif16_pass_smem<6>(buf, t, tid);

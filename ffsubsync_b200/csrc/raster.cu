@@ -14,16 +14,9 @@
 #include <algorithm>
 
 #include "common.cuh"
+#include "raster_math.cuh"
 
 namespace {
-
-__device__ __forceinline__ double scaled_seconds(double t, double ratio) {
-  const double x = __dmul_rn(t, ratio);
-  double whole;
-  const double frac = modf(x, &whole);
-  const long long us = (long long)whole * 1000000LL + __double2ll_rn(__dmul_rn(frac, 1e6));
-  return __ddiv_rn((double)us, 1e6);
-}
 
 struct RasterParams {
   const double* start_s;
@@ -53,13 +46,8 @@ __global__ void __launch_bounds__(256) raster_cues_kernel(RasterParams p) {
   const long long nwarps = (long long)gridDim.x * (blockDim.x >> 5);
   for (long long c = c0 + warp; c < c1; c += nwarps) {
     if (p.keep && !p.keep[c]) continue;
-    const double st = scaled_seconds(p.start_s[c], ratio);
-    const double en = scaled_seconds(p.end_s[c], ratio);
-    long long first = __double2ll_rn(__dmul_rn(__dsub_rn(st, p.start_seconds), (double)p.sample_rate));
-    long long last = first + __double2ll_rn(__dmul_rn(__dsub_rn(en, st), (double)p.sample_rate));
-    // Python slice normalisation on a length-n array
-    if (first < 0) { first += n; if (first < 0) first = 0; } else if (first > n) first = n;
-    if (last < 0) { last += n; if (last < 0) last = 0; } else if (last > n) last = n;
+    long long first, last;
+    b2_cue_bounds(p.start_s[c], p.end_s[c], ratio, p.start_seconds, p.sample_rate, n, first, last);
     for (long long i = first + lane; i < last; i += 32) out[i] = level;
   }
 }

@@ -478,6 +478,65 @@ def test_sync_batch_small_vs_oracle(handle):
             del os.environ["B2_SUBBATCHES"]
         assert np.array_equal(r[0], bs) and np.array_equal(r[1], bo) and np.array_equal(r[2], bk)
         assert np.array_equal(r[3], a_s) and np.array_equal(r[4], a_o)
+    # rasterise-to-HBM fallback (float subtitle signals) vs the default in-kernel rasterisation
+    for env in ({"B2_FUSED_RASTER": "0"}, {"B2_FUSED_RASTER": "0", "B2_SUBBATCHES": "2"}):
+        os.environ.update(env)
+        try:
+            r = handle.sync_batch(pcm, pcm_off, 16000, 100, 0.0, 100000, -1, -1, np.concatenate(cs),
+                                  np.concatenate(ce), None, cue_off, grid, 0.0, 6000, want_all=True)
+        finally:
+            for k_ in env:
+                del os.environ[k_]
+        assert np.array_equal(r[0], bs) and np.array_equal(r[1], bo) and np.array_equal(r[2], bk)
+        assert np.array_equal(r[3], a_s) and np.array_equal(r[4], a_o)
+
+
+@pytest.mark.gpu
+def test_sync_batch_fused_raster_edge_cases(handle):
+    """In-kernel rasterisation against the oracle where the cue arithmetic is awkward: dropped
+    (metadata) cues, cues past the end / before the start (Python slice wrap), overlapping and
+    zero-length cues, a pair without cues, and a pair with more cues than the kernel's table
+    (falls back to the rasterise-to-HBM path for the whole call)."""
+    grid = cases.ratio_grid()
+    fpw = 160
+    rs = np.random.RandomState(77)
+
+    def build(n_big):
+        cls_all, pcm_off, cs, ce, keep, cue_off = [], [0], [], [], [], [0]
+        for b, dur in enumerate((90.0, 140.0, 60.0, 75.0)):
+            n = int(dur * 100)
+            cls = (rs.rand(n) < 0.45).astype(np.uint8)
+            cls = np.repeat(cls[::20], 20)[:n]            # 0.2 s runs of speech / silence
+            if b == 2:
+                st, en, kp = np.zeros(0), np.zeros(0), np.zeros(0, np.uint8)
+            else:
+                m = n_big if b == 3 else 60
+                st = np.sort(rs.uniform(-3.0, dur + 8.0, m))
+                en = st + rs.uniform(0.0, 2.5, m)
+                en[::7] = st[::7]                            # zero-length
+                st[1::11] -= 0.004999                        # microsecond rounding boundary cases
+                kp = (rs.rand(m) > 0.15).astype(np.uint8)
+            cls_all.append(cls)
+            pcm_off.append(pcm_off[-1] + n * fpw)
+            cs.append(st); ce.append(en); keep.append(kp)
+            cue_off.append(cue_off[-1] + len(st))
+        pcm = vo.synth_pcm(np.concatenate(cls_all), fpw, seed=5)
+        return pcm, pcm_off, cs, ce, keep, cue_off
+
+    for n_big in (300, 4500):                               # 4500 > 4096: whole call unfused
+        pcm, pcm_off, cs, ce, keep, cue_off = build(n_big)
+        bs, bo, bk, a_s, a_o = handle.sync_batch(
+            pcm, pcm_off, 16000, 100, 0.0, 100000, -1, -1, np.concatenate(cs), np.concatenate(ce),
+            np.concatenate(keep), cue_off, grid, 0.0, 3000, want_all=True)
+        for b in range(4):
+            ref_sig = vo.energy_zcr_detect(pcm[pcm_off[b]:pcm_off[b + 1]], 100, 16000, 0.0)
+            subs = [ro.rasterize(cs[b], ce[b], keep[b].astype(bool), 100, 0, r)[0] for r in grid]
+            results = [ao.fft_align(ref_sig, s, 3000) for s in subs]
+            for kk, (ws, wo) in enumerate(results):
+                assert a_o[b * len(grid) + kk] == wo, (n_big, b, kk)
+                assert _score_ok(a_s[b * len(grid) + kk], ws)
+            wk = ao.max_score_select(results, 3000)
+            assert (bk[b], bo[b]) == (wk, results[wk][1])
 
 
 def test_serialized_speech_replay_batch(handle, tmp_path):
