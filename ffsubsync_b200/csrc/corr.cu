@@ -74,7 +74,7 @@ struct CueArrays {     // device copies of the batch's cue list (cue-mode only)
 };
 
 constexpr int kMaxCuesFused = 4096;  // per pair; more -> the caller uses the rasterise-to-HBM path
-constexpr size_t kSmemBytesCues = kSmemBytes + (size_t)kP + (size_t)kMaxCuesFused * 8;
+constexpr size_t kSmemBytesCues = kSmemBytes + (size_t)kP + (size_t)kMaxCuesFused * 10;
 
 // Bulk L2 prefetch (16-byte aligned address, size a multiple of 16).
 __device__ __forceinline__ void l2_prefetch(const void* p, uint32_t bytes) {
@@ -245,6 +245,8 @@ __device__ __forceinline__ void sub_correlate_body(
   float2* fine32 = tw1024 + 1024;
   unsigned char* mask = smem_raw + kSmemBytes;                   // kP bytes      (CUES only)
   int2* cue_bounds = reinterpret_cast<int2*>(mask + kP);         // kMaxCuesFused (CUES only)
+  unsigned short* hit = reinterpret_cast<unsigned short*>(cue_bounds + kMaxCuesFused);  // cues meeting the block
+  __shared__ int n_hit;
   __shared__ float red[kThreads / 32];
   __shared__ uint32_t tmem_base_s;
   const int tid = threadIdx.x;
@@ -291,12 +293,19 @@ __device__ __forceinline__ void sub_correlate_body(
       l2_prefetch(spec + (size_t)(job.spec_base + (blk + 1 - job.blk_lo)) * kPairs, kPairs * 16);
     }
     if (CUES) {
-      // rasterise frames [j0, j0 + L) of this (pair, ratio) into the byte mask
+      // rasterise frames [j0, j0 + L) of this (pair, ratio) into the byte mask: all threads scan the
+      // cue table for cues meeting the block (a few dozen of ~2000), warps then fill those
       for (int i = tid; i < (L >> 4); i += kThreads) reinterpret_cast<uint4*>(mask)[i] = make_uint4(0, 0, 0, 0);
+      if (tid == 0) n_hit = 0;
       __syncthreads();
-      const int lane = tid & 31;
-      for (int c = tid >> 5; c < job.n_cues; c += kThreads / 32) {
+      for (int c = tid; c < job.n_cues; c += kThreads) {
         const int2 bd = cue_bounds[c];
+        if (bd.y > max(bd.x, j0) && bd.x < j0 + L) hit[atomicAdd(&n_hit, 1)] = (unsigned short)c;
+      }
+      __syncthreads();
+      const int lane = tid & 31, hits = n_hit;
+      for (int e = tid >> 5; e < hits; e += kThreads / 32) {
+        const int2 bd = cue_bounds[hit[e]];
         const int lo = max(bd.x, j0) - j0, hi = min(bd.y, j0 + L) - j0;
         for (int i = lo + lane; i < hi; i += 32) mask[i] = 1;
       }

@@ -531,9 +531,20 @@ def test_sync_batch_fused_raster_edge_cases(handle):
         for b in range(4):
             ref_sig = vo.energy_zcr_detect(pcm[pcm_off[b]:pcm_off[b + 1]], 100, 16000, 0.0)
             subs = [ro.rasterize(cs[b], ce[b], keep[b].astype(bool), 100, 0, r)[0] for r in grid]
-            results = [ao.fft_align(ref_sig, s, 3000) for s in subs]
+            if len(cs[b]) == 0:
+                # all-zero 2-frame signal: thousands of offsets tie exactly and the reference's pick is
+                # FFT round-off; the defined answer is the exact argmax (largest offset among equals)
+                results = [ao.exact_align(ref_sig, s, 3000) for s in subs]
+            else:
+                results = [ao.fft_align(ref_sig, s, 3000) for s in subs]
             for kk, (ws, wo) in enumerate(results):
-                assert a_o[b * len(grid) + kk] == wo, (n_big, b, kk)
+                go = int(a_o[b * len(grid) + kk])
+                if go != wo:
+                    # random signals, integer-valued scores: only an exact tie (which the reference
+                    # breaks by FFT round-off, this path by np.argmax order on exact values) may differ
+                    assert ao.exact_score(ref_sig, subs[kk], go) == ao.exact_score(ref_sig, subs[kk], wo)
+                    assert go > wo, (n_big, b, kk)
+                    results[kk] = (ws, go)
                 assert _score_ok(a_s[b * len(grid) + kk], ws)
             wk = ao.max_score_select(results, 3000)
             assert (bk[b], bo[b]) == (wk, results[wk][1])
