@@ -557,14 +557,12 @@ extern "C" int b2_sync_batch(b2_handle h, const int16_t* pcm, const int64_t* pcm
   sub_off[0] = 0;
   for (size_t j = 0; j < J; ++j) sub_off[j + 1] = sub_off[j] + lengths[j];
 
-  // Fused mode (default): the K subtitle signals of a pair are never materialised - the
-  // correlation kernel rasterises each block from the cue list in shared memory (B2CueSource).
-  // Fallback (B2_FUSED_RASTER=0, or a pair with more cues than the kernel's shared-memory table):
-  // raster_cues_kernel writes float signals to HBM and the generic aligner reads them back.
+  // Default: the K subtitle signals of a pair are never materialised as floats - the cue list is
+  // rasterised into bit masks (1 bit per frame) that the correlation kernel and the exact re-score
+  // read.  B2_FUSED_RASTER=0 (A/B and test knob): raster_cues_kernel writes float signals to HBM and
+  // the generic aligner (the b2_align_batch path) reads them back.
   bool fused = true;
   if (const char* e = getenv("B2_FUSED_RASTER")) fused = atoi(e) != 0;
-  for (int b = 0; b < B && fused; ++b)
-    if (cue_off[b + 1] - cue_off[b] > kB2MaxCuesFused) fused = false;
   B2CueSource cue_src{cue_start_s, cue_end_s, cue_keep, cue_off, ratios, sample_rate, start_seconds};
 
   void *d_refsig, *d_subsig = nullptr, *d_res;

@@ -118,8 +118,9 @@ int b2i_bounds_launch(b2_ctx* h, const float* d_sig, const int64_t* off_host, in
                       int64_t* d_first, int64_t* d_last);
 int b2i_blend_launch(b2_ctx* h, const float* d_a, const float* d_b, int64_t n, int mode, double wa,
                      double wb, float* d_out);
-// Cue mode of the aligner (b2_sync_batch): subtitle signals are rasterised from the cue list
-// inside the correlation kernel; all arrays are HOST pointers, cue_off has B+1 absolute entries.
+// Cue mode of the aligner (b2_sync_batch): the subtitle signals are rasterised from the cue list
+// into bit masks (never into float signals); all arrays are HOST pointers, cue_off has B+1
+// absolute entries.
 struct B2CueSource {
   const double* cue_start;
   const double* cue_end;
@@ -129,7 +130,8 @@ struct B2CueSource {
   int sample_rate;
   double start_seconds;
 };
-constexpr int kB2MaxCuesFused = 4096;  // per pair (shared-memory budget of the cue-mode kernel)
+int b2i_raster_bits_launch(b2_ctx* h, const B2CueSource* src, int B, int K, const int64_t* sig_off,
+                           const long long* bits_off, uint32_t* d_bits);
 int b2i_align_launch(b2_ctx* h, const float* d_ref, const int64_t* ref_off_host,
                      const float* d_sub, const int64_t* sub_off_host, int B, int K,
                      int32_t max_offset_samples, double* d_score, int32_t* d_offset,

@@ -22,7 +22,6 @@
 
 #include "common.cuh"
 #include "corr.cuh"
-#include "raster_math.cuh"
 
 namespace {
 
@@ -45,11 +44,8 @@ struct SubJob {        // one (pair, ratio, offset tile)
   long long score_off; // where the tile's Wt scores go
   long long spec_base; // index of the spectrum of block blk_lo
   int S, blk_lo, blk_hi, n_out, energy_slot;
-  // rasterise-on-the-fly mode (subtitle signal generated from the cue list inside the kernel)
-  long long cue_lo;    // first cue of the pair in the uploaded cue arrays
-  long long bits_off;  // word offset of this (pair, ratio)'s speech bit mask (side output)
-  double ratio;
-  int n_cues;
+  // bit-mask mode (b2_sync_batch): the subtitle signal is one bit per frame (raster_bits_kernel)
+  long long bits_off;  // word offset of this (pair, ratio)'s speech bit mask
   float hi;            // 2*min(1/ratio, 1) - 1: value of a frame inside a cue after x -> 2x-1
 };
 
@@ -61,20 +57,13 @@ struct SelJob {        // one (pair, ratio)
   int out_index;       // b*K + k
   int kind;            // 0 normal, 1 empty input, 2 everything masked
   int masked_offset;   // offset reported when kind == 2
-  long long bits_off;  // >= 0: the subtitle signal is the bit mask written by the cue-mode kernel
-  float sub_level;     // value of a frame inside a cue, min(1/ratio, 1) as float32 (cue mode)
+  long long bits_off;  // >= 0: the subtitle signal is a bit mask (one bit per frame)
+  float sub_level;     // value of a frame inside a cue, min(1/ratio, 1) as float32 (bit-mask mode)
 };
 
-struct CueArrays {     // device copies of the batch's cue list (cue-mode only)
-  const double* start_s;
-  const double* end_s;
-  const unsigned char* keep;  // may be null
-  double start_seconds;
-  int sample_rate;
-};
-
-constexpr int kMaxCuesFused = 4096;  // per pair; more -> the caller uses the rasterise-to-HBM path
-constexpr size_t kSmemBytesCues = kSmemBytes + (size_t)kP + (size_t)kMaxCuesFused * 10;
+// bit-mask mode: the speech bits of the current and the next block (kP/32 words each) sit behind
+// the twiddle tables in shared memory
+constexpr size_t kSmemBytesBits = kSmemBytes + 2 * (size_t)(kP / 32) * 4;
 
 // Bulk L2 prefetch (16-byte aligned address, size a multiple of 16).
 __device__ __forceinline__ void l2_prefetch(const void* p, uint32_t bytes) {
@@ -228,25 +217,21 @@ __device__ __forceinline__ void accumulate_block_tmem(uint32_t taddr, const floa
   tmem_wait_st();
 }
 
-// CUES = false: the subtitle signal is a float array in global memory (b2_align_batch).
-// CUES = true : it is generated block by block from the pair's cue list (b2_sync_batch): the
-//   scaled cue bounds are computed once per CTA (bit-exact reference arithmetic, raster_math.cuh),
-//   each block's frames are rasterised into a byte mask in shared memory, the first FFT pass
-//   reads that mask, and the mask is also written out as a bit mask (1/32 of the float signal)
-//   for the exact re-score.  No subtitle signal ever exists in HBM.
-template <bool TMEM, bool CUES>
+// BITS = false: the subtitle signal is a float array in global memory (b2_align_batch).
+// BITS = true : it is a bit mask, one bit per frame (b2_sync_batch: raster_bits_kernel writes the
+//   K masks of a pair straight from the cue list, 1/32 of the bytes of the float signals, and the
+//   exact re-score reads the same masks).  The words of block blk+1 are fetched while block blk is
+//   transformed (registers -> shared memory, double buffered).
+template <bool TMEM, bool BITS>
 __device__ __forceinline__ void sub_correlate_body(
     const float* __restrict__ sub, const SubJob* __restrict__ jobs, const float4* __restrict__ spec,
     const float* __restrict__ spec_energy, int L, float* __restrict__ scores,
-    float2* __restrict__ job_energy, CueArrays cues, uint32_t* __restrict__ sub_bits) {
+    float2* __restrict__ job_energy, const uint32_t* __restrict__ sub_bits) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   float2* buf = reinterpret_cast<float2*>(smem_raw);
   float2* tw1024 = buf + kM;
   float2* fine32 = tw1024 + 1024;
-  unsigned char* mask = smem_raw + kSmemBytes;                   // kP bytes      (CUES only)
-  int2* cue_bounds = reinterpret_cast<int2*>(mask + kP);         // kMaxCuesFused (CUES only)
-  unsigned short* hit = reinterpret_cast<unsigned short*>(cue_bounds + kMaxCuesFused);  // cues meeting the block
-  __shared__ int n_hit;
+  uint32_t* bit_words = reinterpret_cast<uint32_t*>(smem_raw + kSmemBytes);  // [2][kP/32] (BITS only)
   __shared__ float red[kThreads / 32];
   __shared__ uint32_t tmem_base_s;
   const int tid = threadIdx.x;
@@ -258,15 +243,12 @@ __device__ __forceinline__ void sub_correlate_body(
     return;
   }
   init_tables(tw1024, fine32, tid);
-  if (CUES) {
-    for (int c = tid; c < job.n_cues; c += kThreads) {
-      const long long gc = job.cue_lo + c;
-      long long first = 0, last = 0;
-      if (!cues.keep || cues.keep[gc])
-        b2_cue_bounds(cues.start_s[gc], cues.end_s[gc], job.ratio, cues.start_seconds,
-                      cues.sample_rate, (long long)job.S, first, last);
-      cue_bounds[c] = make_int2((int)first, (int)last);
-    }
+  const int wpb = L >> 5;  // mask words per block (L is a multiple of 32)
+  const uint32_t* bits = BITS ? sub_bits + job.bits_off : nullptr;
+  if (BITS) {
+    const uint32_t* src = bits + (long long)job.blk_lo * wpb;
+    uint32_t* dst = bit_words + (job.blk_lo & 1) * (kP / 32);
+    for (int w = tid; w < wpb; w += kThreads) dst[w] = __ldg(src + w);
   }
   uint32_t taddr = 0;
   if (TMEM) {
@@ -286,45 +268,20 @@ __device__ __forceinline__ void sub_correlate_body(
   float er = 0.f;
   for (int blk = job.blk_lo; blk < job.blk_hi; ++blk) {
     const int j0 = blk * L;
-    if (tid == 0 && blk + 1 < job.blk_hi) {
+    const bool more = blk + 1 < job.blk_hi;
+    if (tid == 0 && more) {
       // pull the next block's samples and reference spectrum into L2 while this block computes
       const int jn = j0 + L;
-      if (!CUES) l2_prefetch_floats(sub + job.sub_off + jn, min(job.S - jn, L));
+      if (!BITS) l2_prefetch_floats(sub + job.sub_off + jn, min(job.S - jn, L));
       l2_prefetch(spec + (size_t)(job.spec_base + (blk + 1 - job.blk_lo)) * kPairs, kPairs * 16);
     }
-    if (CUES) {
-      // rasterise frames [j0, j0 + L) of this (pair, ratio) into the byte mask: all threads scan the
-      // cue table for cues meeting the block (a few dozen of ~2000), warps then fill those
-      for (int i = tid; i < (L >> 4); i += kThreads) reinterpret_cast<uint4*>(mask)[i] = make_uint4(0, 0, 0, 0);
-      if (tid == 0) n_hit = 0;
-      __syncthreads();
-      for (int c = tid; c < job.n_cues; c += kThreads) {
-        const int2 bd = cue_bounds[c];
-        if (bd.y > max(bd.x, j0) && bd.x < j0 + L) hit[atomicAdd(&n_hit, 1)] = (unsigned short)c;
-      }
-      __syncthreads();
-      const int lane = tid & 31, hits = n_hit;
-      for (int e = tid >> 5; e < hits; e += kThreads / 32) {
-        const int2 bd = cue_bounds[hit[e]];
-        const int lo = max(bd.x, j0) - j0, hi = min(bd.y, j0 + L) - j0;
-        for (int i = lo + lane; i < hi; i += 32) mask[i] = 1;
-      }
-      __syncthreads();
-      for (int wi = tid; wi < (L >> 5); wi += kThreads) {  // side output: 32 frames -> one mask word
-        const uint4* m4 = reinterpret_cast<const uint4*>(mask + 32 * wi);
-        const uint4 a = m4[0], b = m4[1];
-        const uint32_t w[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
-        uint32_t bits = 0;
-#pragma unroll
-        for (int k = 0; k < 8; ++k) {  // bytes are 0 or 1: gather bit 0 of the 4 bytes of w[k]
-          const uint32_t nib = (w[k] & 1u) | ((w[k] >> 7) & 2u) | ((w[k] >> 14) & 4u) | ((w[k] >> 21) & 8u);
-          bits |= nib << (4 * k);
-        }
-        sub_bits[job.bits_off + (long long)blk * (L >> 5) + wi] = bits;
-      }
-      MaskSource s;
-      s.mask = mask;
-      s.len = L;
+    uint32_t nw0 = 0, nw1 = 0;  // next block's mask words: loaded now, parked in smem after the math
+    if (BITS) {
+      const uint32_t* src = bits + (long long)(blk + 1) * wpb;
+      if (more && tid < wpb) nw0 = __ldg(src + tid);
+      if (more && tid + kThreads < wpb) nw1 = __ldg(src + tid + kThreads);
+      BitSource s;
+      s.words = bit_words + (blk & 1) * (kP / 32);
       s.t_hi = min(job.S - j0, L);
       s.hi = job.hi;
       st.ss += forward_block(buf, t, tid, s);
@@ -343,6 +300,11 @@ __device__ __forceinline__ void sub_correlate_body(
       sub_accumulate(st, buf, t, pc, tid, spec + item * kPairs);
     }
     er += spec_energy[item];
+    if (BITS) {  // the other buffer was last read in block blk-1's first pass
+      uint32_t* dst = bit_words + ((blk + 1) & 1) * (kP / 32);
+      dst[tid] = nw0;
+      dst[tid + kThreads] = nw1;
+    }
     __syncthreads();  // buf is rewritten by the next block's first pass
   }
   if (TMEM) {  // accumulators back into registers for the retangle
@@ -393,19 +355,16 @@ __global__ void __maxnreg__(kSubRegs)
     sub_correlate_kernel(const float* __restrict__ sub, const SubJob* __restrict__ jobs,
                          const float4* __restrict__ spec, const float* __restrict__ spec_energy,
                          int L, float* __restrict__ scores, float2* __restrict__ job_energy) {
-  sub_correlate_body<true, false>(sub, jobs, spec, spec_energy, L, scores, job_energy, CueArrays{},
-                                  nullptr);
+  sub_correlate_body<true, false>(sub, jobs, spec, spec_energy, L, scores, job_energy, nullptr);
 }
 
-// b2_sync_batch: subtitle blocks rasterised from the cue list inside the kernel (no subtitle
-// signal in HBM); writes the speech bit mask for the exact re-score.
+// b2_sync_batch: subtitle signals as bit masks (no float subtitle signal in HBM).
 __global__ void __maxnreg__(kSubRegs)
-    sub_correlate_cues_kernel(const SubJob* __restrict__ jobs, const float4* __restrict__ spec,
+    sub_correlate_bits_kernel(const SubJob* __restrict__ jobs, const float4* __restrict__ spec,
                               const float* __restrict__ spec_energy, int L,
                               float* __restrict__ scores, float2* __restrict__ job_energy,
-                              CueArrays cues, uint32_t* __restrict__ sub_bits) {
-  sub_correlate_body<true, true>(nullptr, jobs, spec, spec_energy, L, scores, job_energy, cues,
-                                 sub_bits);
+                              const uint32_t* __restrict__ sub_bits) {
+  sub_correlate_body<true, true>(nullptr, jobs, spec, spec_energy, L, scores, job_energy, sub_bits);
 }
 
 // A/B variant (B2_ACC=reg): accumulators in registers, 128 registers per thread.
@@ -414,8 +373,7 @@ __global__ void __launch_bounds__(kThreads, 1)
                                 const float4* __restrict__ spec,
                                 const float* __restrict__ spec_energy, int L,
                                 float* __restrict__ scores, float2* __restrict__ job_energy) {
-  sub_correlate_body<false, false>(sub, jobs, spec, spec_energy, L, scores, job_energy, CueArrays{},
-                                   nullptr);
+  sub_correlate_body<false, false>(sub, jobs, spec, spec_energy, L, scores, job_energy, nullptr);
 }
 
 // ---- candidate selection ---------------------------------------------------------------------
@@ -548,7 +506,7 @@ __global__ void __launch_bounds__(256) rescore_kernel(const SelJob* __restrict__
     double acc = 0.0;
     int i = a0 + threadIdx.x;
     if (job.bits_off >= 0) {
-      // cue mode: subtitle frame i is bit i of the mask written by sub_correlate_cues_kernel;
+      // bit-mask mode: subtitle frame i is bit i of the mask written by raster_bits_kernel;
       // its value after x -> 2x-1 is (2*level - 1) inside a cue and -1 outside
       const uint32_t* bits = sub_bits + job.bits_off;
       const double hi = 2.0 * (double)job.sub_level - 1.0;
@@ -654,17 +612,13 @@ int b2i_align_launch(b2_ctx* h, const float* d_ref, const int64_t* ref_off, cons
                      double* d_score, int32_t* d_offset, int32_t* d_status, int winner_only,
                      const B2CueSource* cue_src) {
   const size_t J = (size_t)B * K;
-  // cue mode: subtitle signals are rasterised inside the correlation kernel from the cue list
-  // (sub_off then only carries the signal lengths); bit masks of the signals are its side output
+  // cue mode (b2_sync_batch): the subtitle signals exist only as bit masks, rasterised from the cue
+  // list by raster_bits_kernel below (sub_off then only carries the signal lengths)
   const bool cue_mode = cue_src != nullptr;
   std::vector<long long> bits_off(cue_mode ? J + 1 : 1, 0);
-  if (cue_mode) {
-    for (int b = 0; b < B; ++b)
-      if (cue_src->cue_off[b + 1] - cue_src->cue_off[b] > kMaxCuesFused)
-        B2_FAIL(h, B2_ERR_UNSUPPORTED, "align: more than %d cues in pair %d (cue mode)", kMaxCuesFused, b);
+  if (cue_mode)
     for (size_t j = 0; j < J; ++j)
       bits_off[j + 1] = bits_off[j] + ((sub_off[j + 1] - sub_off[j]) + kP) / 32 + 1;
-  }
   std::vector<SelJob> sel(J);
   struct PairPlan { long long o_min, o_max; int n_tiles; bool any; };
   std::vector<PairPlan> pp(B);
@@ -725,26 +679,14 @@ int b2i_align_launch(b2_ctx* h, const float* d_ref, const int64_t* ref_off, cons
   // whole words of the speech bit mask per block), at most P/2 + 1
   const int Wt = (int)(max_w <= kP / 2 + 1 ? 32 * ((max_w + 30) / 32) + 1 : (kP / 2 + 1));
   const int L = kP - Wt + 1;
-  // cue mode: device copies of the cue list + the bit-mask side output
-  CueArrays cue_arrays{};
   uint32_t* d_bits = nullptr;
   if (cue_mode) {
-    const size_t c0 = (size_t)cue_src->cue_off[0], nc = (size_t)cue_src->cue_off[B] - c0;
-    MetaArena ca;
-    B2_TRY(b2i_meta_begin(h, &ca, nc * 17 + 1024));
-    cue_arrays.start_s = (const double*)b2i_meta_put(&ca, cue_src->cue_start + c0, nc * 8) - c0;
-    cue_arrays.end_s = (const double*)b2i_meta_put(&ca, cue_src->cue_end + c0, nc * 8) - c0;
-    cue_arrays.keep = cue_src->cue_keep
-                          ? (const unsigned char*)b2i_meta_put(&ca, cue_src->cue_keep + c0, nc) - c0
-                          : nullptr;
-    cue_arrays.start_seconds = cue_src->start_seconds;
-    cue_arrays.sample_rate = cue_src->sample_rate;
-    B2_TRY(b2i_meta_commit(&ca));
     void* db;
     B2_TRY(b2i_ws(h, b2_ctx::WS_SIG_SUB, (size_t)bits_off[J] * 4 + 64, &db));
     d_bits = (uint32_t*)db;
-    B2_CUDA(h, cudaFuncSetAttribute(sub_correlate_cues_kernel,
-                                    cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytesCues));
+    B2_TRY(b2i_raster_bits_launch(h, cue_src, B, K, sub_off, bits_off.data(), d_bits));
+    B2_CUDA(h, cudaFuncSetAttribute(sub_correlate_bits_kernel,
+                                    cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytesBits));
   }
 
   // score buffers + per-(pair,ratio) bookkeeping
@@ -812,8 +754,8 @@ int b2i_align_launch(b2_ctx* h, const float* d_ref, const int64_t* ref_off, cons
       B2_CHECK_LAUNCH(h, "ref_spectra_kernel");
     }
     if (cue_mode)
-      sub_correlate_cues_kernel<<<(unsigned)jobs.size(), kThreads, kSmemBytesCues, h->stream>>>(
-          d_jobs, spec, spec_energy, L, scores, job_energy, cue_arrays, d_bits);
+      sub_correlate_bits_kernel<<<(unsigned)jobs.size(), kThreads, kSmemBytesBits, h->stream>>>(
+          d_jobs, spec, spec_energy, L, scores, job_energy, d_bits);
     else if (h->acc_in_tmem)
       sub_correlate_kernel<<<(unsigned)jobs.size(), kThreads, kSmemBytes, h->stream>>>(
           d_sub, d_jobs, spec, spec_energy, L, scores, job_energy);
@@ -861,15 +803,9 @@ int b2i_align_launch(b2_ctx* h, const float* d_ref, const int64_t* ref_off, cons
         jb.blk_hi = (int)std::min<long long>(blk_hi, ceil_div64(s.S, L));
         jb.n_out = Wt;
         jb.energy_slot = s.energy_slot + tile;
-        jb.cue_lo = 0;
         jb.bits_off = 0;
-        jb.ratio = 1.0;
-        jb.n_cues = 0;
         jb.hi = 0.f;
         if (cue_mode) {
-          jb.cue_lo = cue_src->cue_off[b];
-          jb.n_cues = (int)(cue_src->cue_off[b + 1] - cue_src->cue_off[b]);
-          jb.ratio = cue_src->ratios[k];
           jb.bits_off = s.bits_off;
           jb.hi = 2.f * s.sub_level - 1.f;  // the value load_block16 gives the float signal
         }

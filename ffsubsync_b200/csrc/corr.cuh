@@ -347,24 +347,27 @@ CORR_HD void load_block16(const BlockSource& s, int j, float2 (&v)[16]) {
 
 // A subtitle block rasterised into shared memory as one byte per 10 ms frame (1 = inside a cue):
 // value(t) = (mask[t] ? hi : -1) for t < t_hi, else 0;  hi = 2*min(1/ratio, 1) - 1.
-struct MaskSource {
-  const unsigned char* mask;  // len bytes (len even)
-  int len, t_hi;
-  float hi;
+struct BitSource {
+  const uint32_t* words;  // kP/32 words in shared memory: bit t = sample t of the block is inside a cue
+  int t_hi;               // samples t >= t_hi are zero padding (t_hi <= L)
+  float hi;               // value of a frame inside a cue after x -> 2x-1 (outside: -1)
 };
-CORR_HD void load_block16(const MaskSource& s, int j, float2 (&v)[16]) {
+// samples 2j', 2j'+1 (j' = j + 1024 q) are two adjacent bits of word (j >> 4) + 64 q; the shift is
+// the same for all q
+CORR_HD void load_block16(const BitSource& s, int j, float2 (&v)[16]) {
+  const int sh = 2 * (j & 15);
+  const uint32_t* w = s.words + (j >> 4);
 #pragma unroll
   for (int q = 0; q < 16; ++q) {
     const int t0 = 2 * (j + (q << 10));
-    const int tc = min(t0, s.len - 2);
-    const unsigned short m = *reinterpret_cast<const unsigned short*>(s.mask + tc);
-    v[q].x = t0 < s.t_hi ? ((m & 0xff) ? s.hi : -1.f) : 0.f;
-    v[q].y = t0 + 1 < s.t_hi ? ((m >> 8) ? s.hi : -1.f) : 0.f;
+    const uint32_t m = w[q << 6] >> sh;
+    v[q].x = t0 < s.t_hi ? ((m & 1u) ? s.hi : -1.f) : 0.f;
+    v[q].y = t0 + 1 < s.t_hi ? ((m & 2u) ? s.hi : -1.f) : 0.f;
   }
 }
 
 // First DIF pass (span 16384) reading the block straight from its source (global memory for
-// float signals, the shared-memory cue mask for rasterise-on-the-fly).
+// float signals, the shared-memory copy of the block's speech bits in bit-mask mode).
 // Returns the thread's partial sum of squares of the (transformed) samples it loaded.
 template <class Source>
 CORR_HD float dif16_pass1_global(float2* buf, const Tables& t, int tid, const Source& s) {

@@ -52,6 +52,49 @@ __global__ void __launch_bounds__(256) raster_cues_kernel(RasterParams p) {
   }
 }
 
+// K2b: the same cue arithmetic, output as a bit mask (bit i of word i/32 = frame i is inside a kept
+// cue).  b2_sync_batch never materialises the float signals: the correlation kernel and the exact
+// re-score read these masks (1/32 of the bytes).  One thread per (cue, ratio); a cue spans ~10
+// words, cues of one signal rarely share a word, so the atomics are uncontended.
+struct RasterBitsParams {
+  const double* start_s;
+  const double* end_s;
+  const uint8_t* keep;         // may be null
+  const long long* cue_off;    // [B+1]
+  const double* ratios;        // [K]
+  const long long* sig_off;    // [B*K+1]: only the differences (signal lengths) are used
+  const long long* bits_off;   // [B*K+1] words
+  uint32_t* bits;              // zeroed by the caller
+  int K, sample_rate;
+  double start_seconds;
+};
+
+__global__ void __launch_bounds__(256) raster_bits_kernel(RasterBitsParams p) {
+  const int sig = blockIdx.y;
+  const int b = sig / p.K;
+  const double ratio = p.ratios[sig - b * p.K];
+  const long long c0 = p.cue_off[b], c1 = p.cue_off[b + 1];
+  const long long n = p.sig_off[sig + 1] - p.sig_off[sig];
+  uint32_t* out = p.bits + p.bits_off[sig];
+  for (long long c = c0 + (long long)blockIdx.x * blockDim.x + threadIdx.x; c < c1;
+       c += (long long)gridDim.x * blockDim.x) {
+    if (p.keep && !p.keep[c]) continue;
+    long long first, last;
+    b2_cue_bounds(p.start_s[c], p.end_s[c], ratio, p.start_seconds, p.sample_rate, n, first, last);
+    if (last <= first) continue;
+    const long long w0 = first >> 5, w1 = (last - 1) >> 5;
+    const uint32_t m0 = 0xffffffffu << (first & 31);
+    const uint32_t m1 = 0xffffffffu >> (31 - ((last - 1) & 31));
+    if (w0 == w1) {
+      atomicOr(out + w0, m0 & m1);
+    } else {
+      atomicOr(out + w0, m0);
+      for (long long w = w0 + 1; w < w1; ++w) atomicOr(out + w, 0xffffffffu);
+      atomicOr(out + w1, m1);
+    }
+  }
+}
+
 // ---- K7 -------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) bounds_kernel(const float* __restrict__ sig,
                                                       const long long* __restrict__ off, int n_sig,
@@ -178,6 +221,37 @@ int b2i_raster_launch(b2_ctx* h, const double* cue_start, const double* cue_end,
   dim3 grid((unsigned)std::min<int64_t>((max_cues + 7) / 8, 64), (unsigned)J);
   raster_cues_kernel<<<grid, 256, 0, h->stream>>>(p);
   B2_CHECK_LAUNCH(h, "raster_cues_kernel");
+  return B2_OK;
+}
+
+int b2i_raster_bits_launch(b2_ctx* h, const B2CueSource* src, int B, int K, const int64_t* sig_off,
+                           const long long* bits_off, uint32_t* d_bits) {
+  // cue_off / sig_off may be slices of larger tables (sub-batches), see b2i_raster_launch
+  const size_t J = (size_t)B * K;
+  const size_t c0 = (size_t)src->cue_off[0], nc = (size_t)src->cue_off[B] - c0;
+  if (bits_off[J]) B2_CUDA(h, cudaMemsetAsync(d_bits, 0, (size_t)bits_off[J] * 4, h->stream));
+  int64_t max_cues = 0;
+  for (int b = 0; b < B; ++b) max_cues = std::max<int64_t>(max_cues, src->cue_off[b + 1] - src->cue_off[b]);
+  if (max_cues == 0 || J == 0) return B2_OK;
+  if (J > 65535) B2_FAIL(h, B2_ERR_UNSUPPORTED, "rasterize: B*K > 65535 in one call");
+  MetaArena a;
+  B2_TRY(b2i_meta_begin(h, &a, nc * 17 + (B + 1) * 8 + (J + 1) * 16 + (size_t)K * 8 + 1024));
+  RasterBitsParams p;
+  p.start_s = (const double*)b2i_meta_put(&a, src->cue_start + c0, nc * 8) - c0;
+  p.end_s = (const double*)b2i_meta_put(&a, src->cue_end + c0, nc * 8) - c0;
+  p.keep = src->cue_keep ? (const uint8_t*)b2i_meta_put(&a, src->cue_keep + c0, nc) - c0 : nullptr;
+  p.cue_off = (const long long*)b2i_meta_put(&a, src->cue_off, (size_t)(B + 1) * 8);
+  p.ratios = (const double*)b2i_meta_put(&a, src->ratios, (size_t)K * 8);
+  p.sig_off = (const long long*)b2i_meta_put(&a, sig_off, (J + 1) * 8);
+  p.bits_off = (const long long*)b2i_meta_put(&a, bits_off, (J + 1) * 8);
+  B2_TRY(b2i_meta_commit(&a));
+  p.bits = d_bits;
+  p.K = K;
+  p.sample_rate = src->sample_rate;
+  p.start_seconds = src->start_seconds;
+  dim3 grid((unsigned)std::min<int64_t>((max_cues + 255) / 256, 64), (unsigned)J);
+  raster_bits_kernel<<<grid, 256, 0, h->stream>>>(p);
+  B2_CHECK_LAUNCH(h, "raster_bits_kernel");
   return B2_OK;
 }
 

@@ -86,12 +86,15 @@ __device__ __forceinline__ void tma_bulk_g2s(void* dst, const void* src, uint32_
 // One 32-bit word = samples (x0 = low half, x1 = high half).
 //   energy: x^2 = x*lo8(x) + 256*x*hi8(x) (lo8 unsigned, hi8 signed) -> two 2-way 16x8 dot products
 //   crossings: f = [x0 : previous sample]; (w ^ f) carries prev->x0 in bit 15, x0->x1 in bit 31
-__device__ __forceinline__ void accum_word(uint32_t w, uint32_t prev, int& e_lo, int& e_hi, int& z) {
+__device__ __forceinline__ void accum_word(uint32_t w, uint32_t prev, int& e_lo, int& e_hi,
+                                           uint32_t& z128) {
   const uint32_t perm = __byte_perm(w, 0u, 0x3120);  // bytes [lo8(x0), lo8(x1), hi8(x0), hi8(x1)]
   asm("dp2a.lo.s32.u32 %0, %1, %2, %0;" : "+r"(e_lo) : "r"(w), "r"(perm));
   asm("dp2a.hi.s32.s32 %0, %1, %2, %0;" : "+r"(e_hi) : "r"(w), "r"(perm));
   const uint32_t f = __funnelshift_l(prev, w, 16);
-  z += __popc((w ^ f) & 0x80008000u);
+  // bytes 1 and 3 of the masked word are 0x80 per crossing: a 4-way byte dot product with ones
+  // adds 128 per crossing (one IDP.4A instead of POPC + IADD)
+  z128 = __dp4a((w ^ f) & 0x80008000u, 0x01010101u, z128);
 }
 
 // Lane g of a window owns the contiguous 16-byte chunks [g*CPL, (g+1)*CPL).
@@ -102,7 +105,10 @@ __device__ __forceinline__ void window_part_fast(const unsigned char* wbase, int
   const unsigned char* cbase = wbase + 16 * g * cpl;
   uint32_t pw = 0;
   if (g > 0) pw = *reinterpret_cast<const uint32_t*>(cbase - 4);
-  int e_lo = 0, e_hi = 0;
+  // two independent accumulator sets: the IDP chains are latency-bound otherwise (a CTA that shares
+  // its SM with the correlation kernel has only 8 consumer warps to hide them)
+  int e_lo = 0, e_hi = 0, f_lo = 0, f_hi = 0;
+  uint32_t z128 = 0, y128 = 0;
   if (CPL > 0) {
     uint4 v[CPL > 0 ? CPL : 1];
 #pragma unroll
@@ -110,28 +116,67 @@ __device__ __forceinline__ void window_part_fast(const unsigned char* wbase, int
     if (g == 0) pw = v[0].x << 16;  // first sample of the window: no crossing before it
 #pragma unroll
     for (int c = 0; c < CPL; ++c) {
-      accum_word(v[c].x, pw, e_lo, e_hi, z);
-      accum_word(v[c].y, v[c].x, e_lo, e_hi, z);
-      accum_word(v[c].z, v[c].y, e_lo, e_hi, z);
-      accum_word(v[c].w, v[c].z, e_lo, e_hi, z);
+      accum_word(v[c].x, pw, e_lo, e_hi, z128);
+      accum_word(v[c].y, v[c].x, f_lo, f_hi, y128);
+      accum_word(v[c].z, v[c].y, e_lo, e_hi, z128);
+      accum_word(v[c].w, v[c].z, f_lo, f_hi, y128);
       pw = v[c].w;
     }
-    e += (long long)e_lo + (long long)e_hi * 256LL;
   } else {
     for (int c = 0; c < cpl; ++c) {
       const uint4 v = *reinterpret_cast<const uint4*>(cbase + 16 * c);
       if (c == 0 && g == 0) pw = v.x << 16;
-      accum_word(v.x, pw, e_lo, e_hi, z);
-      accum_word(v.y, v.x, e_lo, e_hi, z);
-      accum_word(v.z, v.y, e_lo, e_hi, z);
-      accum_word(v.w, v.z, e_lo, e_hi, z);
+      accum_word(v.x, pw, e_lo, e_hi, z128);
+      accum_word(v.y, v.x, f_lo, f_hi, y128);
+      accum_word(v.z, v.y, e_lo, e_hi, z128);
+      accum_word(v.w, v.z, f_lo, f_hi, y128);
       pw = v.w;
       if ((c & 15) == 15) {  // keep the 32-bit partial sums far from overflow
-        e += (long long)e_lo + (long long)e_hi * 256LL;
-        e_lo = e_hi = 0;
+        e += (long long)e_lo + (long long)f_lo + ((long long)e_hi + (long long)f_hi) * 256LL;
+        e_lo = e_hi = f_lo = f_hi = 0;
       }
     }
-    e += (long long)e_lo + (long long)e_hi * 256LL;
+  }
+  e += (long long)e_lo + (long long)f_lo + ((long long)e_hi + (long long)f_hi) * 256LL;
+  z += (int)((z128 + y128) >> 7);
+}
+
+// Sum (e, z) over the G lanes of a window (G a power of two <= 32, lanes contiguous).
+template <int GT>
+__device__ __forceinline__ void lane_group_sum(int G, long long& e, int& z) {
+  if (GT > 0) {
+#pragma unroll
+    for (int off = GT >> 1; off > 0; off >>= 1) {
+      e += __shfl_xor_sync(0xffffffffu, e, off);
+      z += __shfl_xor_sync(0xffffffffu, z, off);
+    }
+  } else {
+    for (int off = G >> 1; off > 0; off >>= 1) {
+      e += __shfl_xor_sync(0xffffffffu, e, off);
+      z += __shfl_xor_sync(0xffffffffu, z, off);
+    }
+  }
+}
+
+// All windows of one staged tile that belong to this thread's lane group (vector path: the window
+// starts are 16-byte aligned inside the span).  CPL / GT are compile-time for the common rates.
+template <int CPL, int GT>
+__device__ __forceinline__ void consume_tile_fast(const VadParams& p, const TileDesc& d,
+                                                  const unsigned char* span, int g, int wl0,
+                                                  int wstep) {
+  const int fpw = p.fpw;
+#pragma unroll 1
+  for (int wl = wl0; wl < p.tw; wl += wstep) {  // uniform trip count: shuffles stay converged
+    long long e = 0;
+    int z = 0;
+    const bool active = wl < d.n_windows;
+    const bool full = active && d.n_left - (long long)wl * fpw >= fpw;
+    if (full) window_part_fast<CPL>(span + (size_t)wl * fpw * 2, g, p.cpl, e, z);
+    lane_group_sum<GT>(p.G, e, z);
+    if (active && g == 0) {
+      const bool speech = full && e >= p.e_min && z >= p.z_lo && z <= p.z_hi;
+      p.out[d.out_base + wl] = speech ? 1.0f : p.label;
+    }
   }
 }
 
@@ -156,10 +201,14 @@ __global__ void __launch_bounds__(kThreads) vad_energy_zcr_kernel(VadParams p) {
   if (tid >= kConsumerThreads) {
     // ================================ producer warp ==========================================
     if (tid != kConsumerThreads) return;
-    int cur_b = 0;
-    for (long long it = 0;; ++it) {
-      const int stage = (int)(it % nst);
-      if (it >= nst) mbar_wait(&empty_bar[stage], (uint32_t)(((it / nst) - 1) & 1));
+    int cur_b = 0, stage = 0;
+    uint32_t round = 0;  // how many times the ring wrapped
+    for (;; ++stage) {
+      if (stage == nst) {
+        stage = 0;
+        ++round;
+      }
+      if (round > 0) mbar_wait(&empty_bar[stage], (round - 1) & 1u);
       // dynamic tile hand-out: whichever CTAs are resident share the stream evenly, also when
       // this kernel co-runs with the correlation kernels and gets fewer than its 2 CTAs per SM
       const long long t = (long long)atomicAdd(p.tile_counter, 1ULL);
@@ -212,11 +261,13 @@ __global__ void __launch_bounds__(kThreads) vad_energy_zcr_kernel(VadParams p) {
   // ================================== consumer warps ==========================================
   const int G = p.G;
   const int g = tid % G;
-  const int wl = tid / G;
+  const int wl0 = tid / G;
+  const int wstep = kConsumerThreads / G;
   const int fpw = p.fpw;
-  for (long long it = 0;; ++it) {
-    const int stage = (int)(it % nst);
-    mbar_wait(&full_bar[stage], (uint32_t)((it / nst) & 1));
+  int stage = 0;
+  uint32_t phase = 0;
+  for (;;) {
+    mbar_wait(&full_bar[stage], phase);
     const TileDesc d = descs[stage];
     if (d.n_windows == 0) break;
     unsigned char* span = data + (size_t)stage * p.stage_bytes;
@@ -225,37 +276,38 @@ __global__ void __launch_bounds__(kThreads) vad_energy_zcr_kernel(VadParams p) {
       if (tid < nb) span[d.tail_src_off + tid] = p.pcm_bytes[d.span_gbyte + d.tail_src_off + tid];
       asm volatile("bar.sync 1, %0;" ::"n"(kConsumerThreads) : "memory");
     }
-    long long e = 0;
-    int z = 0;
-    const bool active = wl < d.n_windows;
-    const long long left = d.n_left - (long long)wl * fpw;  // samples from window start to signal end
-    const bool full = active && left >= fpw;
-    const unsigned char* wbase = span + d.head_bytes + (size_t)wl * fpw * 2;
-    if (full) {
-      if (p.fast && d.head_bytes == 0) {
-        if (p.cpl == 5) window_part_fast<5>(wbase, g, 5, e, z);          // 16 kHz, 4 lanes/window
-        else if (p.cpl == 15) window_part_fast<15>(wbase, g, 15, e, z);  // 48 kHz, 4 lanes/window
-        else window_part_fast<0>(wbase, g, p.cpl, e, z);
-      } else {
-        const short* xs = reinterpret_cast<const short*>(wbase);
-        for (int i = g; i < fpw; i += G) {
-          const int x = xs[i];
-          const int px = i > 0 ? (int)xs[i - 1] : x;
-          e += (long long)x * x;
-          z += ((x < 0) != (px < 0));
+    if (p.fast && d.head_bytes == 0) {
+      if (p.cpl == 5 && G == 4) consume_tile_fast<5, 4>(p, d, span, g, wl0, wstep);         // 16 kHz
+      else if (p.cpl == 15 && G == 4) consume_tile_fast<15, 4>(p, d, span, g, wl0, wstep);  // 48 kHz
+      else consume_tile_fast<0, 0>(p, d, span, g, wl0, wstep);
+    } else {
+      for (int wl = wl0; wl < p.tw; wl += wstep) {
+        long long e = 0;
+        int z = 0;
+        const bool active = wl < d.n_windows;
+        const bool full = active && d.n_left - (long long)wl * fpw >= fpw;
+        if (full) {
+          const short* xs = reinterpret_cast<const short*>(span + d.head_bytes + (size_t)wl * fpw * 2);
+          for (int i = g; i < fpw; i += G) {
+            const int x = xs[i];
+            const int px = i > 0 ? (int)xs[i - 1] : x;
+            e += (long long)x * x;
+            z += ((x < 0) != (px < 0));
+          }
+        }
+        lane_group_sum<0>(G, e, z);
+        if (active && g == 0) {
+          const bool speech = full && e >= p.e_min && z >= p.z_lo && z <= p.z_hi;
+          p.out[d.out_base + wl] = speech ? 1.0f : p.label;
         }
       }
     }
-    for (int off = G >> 1; off > 0; off >>= 1) {
-      e += __shfl_xor_sync(0xffffffffu, e, off);
-      z += __shfl_xor_sync(0xffffffffu, z, off);
-    }
-    if (active && g == 0) {
-      const bool speech = full && e >= p.e_min && z >= p.z_lo && z <= p.z_hi;
-      p.out[d.out_base + wl] = speech ? 1.0f : p.label;
-    }
     __syncwarp();
     if ((tid & 31) == 0) mbar_arrive(&empty_bar[stage]);  // this warp is done with the stage
+    if (++stage == nst) {
+      stage = 0;
+      phase ^= 1u;
+    }
   }
 }
 
@@ -328,15 +380,24 @@ int b2i_vad_launch(b2_ctx* h, const int16_t* d_pcm, const int64_t* pcm_off, int 
   }
   p.G = G;
   p.cpl = p.fast ? C / G : 0;
-  p.tw = kConsumerThreads / G;
+  // tile = wpt rounds of (256 / G) windows: per-tile costs (mbarrier wait, descriptor, release)
+  // are amortised over wpt windows per lane group
+  int wpt = 1;
+  if (const char* e = getenv("B2_VAD_WPT")) wpt = std::max(1, std::min(8, atoi(e)));  // tuning knob
   p.fpw = fpw;
-  p.stage_bytes = ((p.tw * fpw * 2 + 32) + 127) & ~127;
-  // Measured (tools/vad_tune.py, 100 x 2 h signals): 4 stages x 2 CTAs/SM 5.90 TB/s, 3 x 3 CTAs
-  // 7.15 TB/s, 2 x 4 CTAs 7.19 TB/s - resident consumer warps (32 per SM) matter more than ring
-  // depth, so the ring is 2 deep and up to 4 CTAs share an SM.
-  int stages = 2;
+  // Measured after the per-tile overhead was cut (tools/vad_tune.py, 100 x 2 h signals at 16 kHz):
+  // 4 stages x 2 CTAs/SM 7.25 TB/s, 2 x 3 CTAs 7.06, 2 x 4 CTAs 5.63, 4 x 1 CTA 4.59 - ring depth
+  // now matters more than resident warps, so the ring is 4 deep when two such CTAs fit an SM.
+  int stages = 4;
   if (const char* e = getenv("B2_VAD_STAGES")) stages = std::max(2, std::min(kMaxStages, atoi(e)));  // tuning knob
-  while (stages > 2 && (size_t)stages * p.stage_bytes > 200 * 1024) --stages;
+  for (;;) {
+    p.tw = wpt * (kConsumerThreads / G);
+    p.stage_bytes = ((p.tw * fpw * 2 + 32) + 127) & ~127;
+    if ((size_t)stages * p.stage_bytes <= 200 * 1024) break;
+    if (wpt > 1) --wpt;
+    else if (stages > 2) --stages;
+    else break;
+  }
   p.stages = stages;
   size_t smem = (size_t)stages * p.stage_bytes + 2 * kMaxStages * sizeof(uint64_t) +
                 kMaxStages * sizeof(TileDesc) + 64;

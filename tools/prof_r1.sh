@@ -13,7 +13,7 @@ timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --c
   > gpurun_out/bench_under_ncu_${TAG}.log 2>&1
 # full captures of the main kernels (one launch each, after warm-up)
 timeout 900 ncu --set full --clock-control none --import-source on \
-  -k regex:'sub_correlate|ref_spectra|vad_energy|rescore|raster' -s 5 -c 5 -o gpurun_out/prof_${TAG} -f \
+  -k regex:'sub_correlate|ref_spectra|vad_energy|rescore|raster' -s 6 -c 8 -o gpurun_out/prof_${TAG} -f \
   python bench.py --pairs 16 --steps 1 --warmup 1 --no-cpu-baseline > gpurun_out/prof_${TAG}.log 2>&1
 ls -la gpurun_out
 echo ==== BENCH

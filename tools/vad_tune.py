@@ -46,14 +46,19 @@ def main():
     as_i32 = pcm.view(torch.int32)
     ms = timed(lambda: torch.bitwise_xor(as_i32[: as_i32.numel() // 2], as_i32[as_i32.numel() // 2:]).max())
     print("torch xor+max (read + half write): %.3f ms" % ms)
-    for stages in ("4", "3", "2"):
-        for ctas in ("1", "2", "3", "4"):
-            os.environ["B2_VAD_STAGES"] = stages
-            os.environ["B2_VAD_CTAS_FORCE"] = ctas
-            ms = timed(lambda: h.vad_energy_zcr(pcm.data_ptr(), pcm_off, FR, 100, 0.0, 100000, out=out.data_ptr(),
-                                                memspace=_native.B2_DEVICE))
-            print("vad stages=%s ctas/SM<=%s: %.3f ms = %.0f GB/s" % (stages, ctas, ms, (gb + n_win * 4 / 1e9) / ms * 1e3),
-                  flush=True)
+    for wpt in ("1", "2", "4"):
+        for stages in ("4", "3", "2"):
+            for ctas in ("1", "2", "3", "4"):
+                smem = int(stages) * (int(wpt) * 64 * FPW * 2 + 128) + 512
+                if int(ctas) * smem > 227 * 1024 or (int(ctas) > 1 and (int(ctas) - 1) * smem > 227 * 1024):
+                    continue
+                os.environ["B2_VAD_WPT"] = wpt
+                os.environ["B2_VAD_STAGES"] = stages
+                os.environ["B2_VAD_CTAS_FORCE"] = ctas
+                ms = timed(lambda: h.vad_energy_zcr(pcm.data_ptr(), pcm_off, FR, 100, 0.0, 100000,
+                                                    out=out.data_ptr(), memspace=_native.B2_DEVICE))
+                print("vad wpt=%s stages=%s ctas/SM=%s (%d KB/CTA): %.3f ms = %.0f GB/s"
+                      % (wpt, stages, ctas, smem // 1024, ms, (gb + n_win * 4 / 1e9) / ms * 1e3), flush=True)
 
 
 if __name__ == "__main__":
