@@ -7,9 +7,12 @@
   * ``ComputeSpeechFrameBoundariesMixin`` (:299-317), ``DeserializeSpeechTransformer`` (:987-1009),
     ``make_subtitle_speech_pipeline`` (:56-98), ``_is_metadata`` (:928-943).
 
-Out of scope here: ffprobe/embedded-subtitle extraction, silero/webrtc/
-auditok detectors (third-party wheels), multi-segment sampling.  Other detectors can be plugged
-in through ``DETECTOR_FACTORIES`` with the reference's factory signature.
+  * ``MultiSegmentVideoSpeechTransformer`` (:760-903) - sparse reference from a few sampled
+    windows; the windows of an in-memory / raw-PCM reference go through ONE batched VAD launch.
+
+Out of scope here: embedded-subtitle extraction, silero/webrtc/auditok
+detectors (third-party wheels).  Other detectors can be plugged in through
+``DETECTOR_FACTORIES`` with the reference's factory signature.
 """
 import io
 import logging
@@ -17,8 +20,9 @@ import os
 import re
 import shutil
 import subprocess
+from concurrent.futures import ThreadPoolExecutor, as_completed
 from datetime import timedelta
-from typing import Callable, Dict, List, NamedTuple, Optional, Union
+from typing import Callable, Dict, List, NamedTuple, Optional, Tuple, Union
 
 import numpy as np
 
@@ -159,6 +163,18 @@ class ComputeSpeechFrameBoundariesMixin:
 _PCM_SUFFIXES = (".pcm", ".raw", ".s16le")
 
 
+class _BoundedReader:
+    """.read(n) over at most ``limit`` bytes of a file object."""
+
+    def __init__(self, fh, limit: int) -> None:
+        self._fh, self._left = fh, limit
+
+    def read(self, n: int) -> bytes:
+        data = self._fh.read(min(n, self._left)) if self._left > 0 else b""
+        self._left -= len(data)
+        return data
+
+
 class VideoSpeechTransformer(TransformerMixin):
     """PCM -> 100 Hz speech signal.  ``fit`` accepts what the reference accepts (a media path,
     decoded through an ffmpeg subprocess when the binary is available) and, because this layer
@@ -221,18 +237,30 @@ class VideoSpeechTransformer(TransformerMixin):
                  "-ar", str(self.frame_rate), "-"]
         return args
 
+    def _pcm_window(self, n_bytes: int) -> Tuple[int, int]:
+        """Byte range of a raw PCM source that ffmpeg's ``-ss start_seconds -t max_duration_seconds``
+        (speech_transformers.py:688-699) would have decoded."""
+        lo = min(n_bytes, 2 * int(round(self.start_seconds * self.frame_rate)))
+        hi = n_bytes
+        if self.max_duration_seconds is not None:
+            hi = min(hi, lo + 2 * int(round(self.max_duration_seconds * self.frame_rate)))
+        return lo, hi
+
     def _open_source(self, src):
         """-> (readable with .read(n), total_duration_seconds or None, closer)"""
         bytes_per_second = 2.0 * self.frame_rate
         if isinstance(src, np.ndarray):
             src = np.ascontiguousarray(src).view(np.uint8).tobytes() if src.dtype != np.uint8 else src.tobytes()
         if isinstance(src, (bytes, bytearray, memoryview)):
-            return io.BytesIO(bytes(src)), len(src) / bytes_per_second, None
+            lo, hi = self._pcm_window(len(src))
+            return io.BytesIO(bytes(src[lo:hi])), (hi - lo) / bytes_per_second, None
         if hasattr(src, "read"):
             return src, None, None
         if isinstance(src, str) and src.lower().endswith(_PCM_SUFFIXES):
+            lo, hi = self._pcm_window(os.path.getsize(src))
             fh = open(src, "rb")
-            return fh, os.path.getsize(src) / bytes_per_second, fh.close
+            fh.seek(lo)
+            return _BoundedReader(fh, hi - lo), (hi - lo) / bytes_per_second, fh.close
         args = self._build_ffmpeg_args(src)
         if shutil.which(args[0]) is None:
             raise ValueError(
@@ -277,6 +305,179 @@ class VideoSpeechTransformer(TransformerMixin):
                 "Unable to detect speech. "
                 "Perhaps try specifying a different stream / track, or a different vad.")
         self.video_speech_results_ = np.concatenate(media_bstring)
+        logger.info("total of speech segments: %s", np.sum(self.video_speech_results_))
+        return self
+
+    def transform(self, *_) -> np.ndarray:
+        return self.video_speech_results_
+
+
+class MultiSegmentVideoSpeechTransformer(TransformerMixin):
+    """Sparse reference signal from ``segment_count`` short windows spread over the reference
+    (speech_transformers.py:760-903): VAD runs only on the sampled windows, their results are
+    written at their true positions of a full-length array that is zero elsewhere, and the normal
+    ratio search + cross-correlation runs on that.
+
+    Same constructor, ``_segment_starts`` arithmetic, assembly and error behaviour as the
+    reference.  Difference in execution: when the reference audio is raw PCM in memory (or a
+    ``.pcm`` file) and the detector is this package's energy detector, all windows are detected by
+    ONE batched kernel launch (ragged batch of B = len(starts) signals) instead of up to four
+    threads each decoding and detecting one window; other sources / detectors use the
+    reference's thread pool of ``VideoSpeechTransformer`` fits."""
+
+    START_MARGIN_SECONDS: int = 30
+    END_MARGIN_SECONDS: int = 60
+
+    def __init__(
+        self,
+        vad: str,
+        sample_rate: int,
+        frame_rate: int,
+        non_speech_label: float,
+        segment_count: int = 8,
+        segment_duration: int = 60,
+        skip_intro_outro: bool = False,
+        parallel_workers: int = 4,
+        ffmpeg_path: Optional[str] = None,
+        ref_stream: Optional[str] = None,
+        vlc_mode: bool = False,
+        gui_mode: bool = False,
+    ) -> None:
+        # audio-only sampling: a "subs_then_" prefix is dropped (:799-801)
+        self.vad: str = vad.split("subs_then_")[-1]
+        self.sample_rate: int = sample_rate
+        self.frame_rate: int = frame_rate
+        self._non_speech_label: float = non_speech_label
+        self.segment_count: int = segment_count
+        self.segment_duration: int = segment_duration
+        self.skip_intro_outro: bool = skip_intro_outro
+        self.parallel_workers: int = parallel_workers
+        self.ffmpeg_path: Optional[str] = ffmpeg_path
+        self.ref_stream: Optional[str] = ref_stream
+        self.vlc_mode: bool = vlc_mode
+        self.gui_mode: bool = gui_mode
+        self.video_speech_results_: Optional[np.ndarray] = None
+
+    def _segment_starts(self, total_duration: float) -> List[int]:
+        """Whole-second start times, evenly spread over [lo, hi - segment_duration] (:812-830)."""
+        seg = self.segment_duration
+        if total_duration <= seg:
+            return [0]
+        lo = float(self.START_MARGIN_SECONDS) if self.skip_intro_outro else 0.0
+        hi = total_duration - (self.END_MARGIN_SECONDS if self.skip_intro_outro else 0)
+        if hi - lo < seg:  # the margins do not leave room for one segment: drop them
+            lo, hi = 0.0, total_duration
+        room = hi - lo - seg
+        count = max(1, self.segment_count)
+        if room <= 0 or count == 1:
+            return [int(max(0.0, min(lo, total_duration - seg)))]
+        last = int(total_duration) - seg
+        picked = {max(0, min(int(round(lo + i * (room / (count - 1)))), last)) for i in range(count)}
+        return sorted(picked)
+
+    # -- reference duration -----------------------------------------------------------------------
+    def _pcm_bytes_of(self, src) -> Optional[int]:
+        if isinstance(src, np.ndarray):
+            return src.size * src.dtype.itemsize
+        if isinstance(src, (bytes, bytearray, memoryview)):
+            return len(src)
+        if isinstance(src, str) and src.lower().endswith(_PCM_SUFFIXES):
+            return os.path.getsize(src)
+        return None
+
+    def _probe_duration(self, fname) -> float:
+        n_bytes = self._pcm_bytes_of(fname)
+        try:
+            if n_bytes is not None:
+                return n_bytes / (2.0 * self.frame_rate)
+            exe = os.path.join(self.ffmpeg_path, "ffprobe") if self.ffmpeg_path else "ffprobe"
+            if shutil.which(exe) is None:
+                raise RuntimeError("no ffprobe binary found")
+            out = subprocess.check_output(
+                [exe, "-v", "error", "-show_entries", "format=duration", "-of",
+                 "default=noprint_wrappers=1:nokey=1", fname], stderr=subprocess.DEVNULL)
+            return float(out.decode().strip())
+        except Exception as e:
+            raise ValueError("multi-segment sync needs the reference duration, but probing "
+                             "'%s' failed: %s" % (fname, e))
+
+    # -- per-segment detection ----------------------------------------------------------------------
+    def _extract_segment_speech(self, fname, start: int) -> Tuple[int, np.ndarray]:
+        """One window through its own VideoSpeechTransformer (:832-847)."""
+        segment = VideoSpeechTransformer(
+            vad=self.vad, sample_rate=self.sample_rate, frame_rate=self.frame_rate,
+            non_speech_label=self._non_speech_label, start_seconds=start,
+            ffmpeg_path=self.ffmpeg_path, ref_stream=self.ref_stream, vlc_mode=self.vlc_mode,
+            gui_mode=self.gui_mode, max_duration_seconds=self.segment_duration)
+        segment.fit(fname)
+        return start, segment.transform()
+
+    def _batched_params(self):
+        """(z_lo, z_hi) when ``self.vad`` names the plain energy detectors, else None."""
+        if "fused" in self.vad:
+            return None
+        if "energy_only" in self.vad:
+            return 0, int((1.0 / self.sample_rate) * self.frame_rate + 0.5)
+        if "energy" in self.vad and DETECTOR_FACTORIES.get("energy") is _make_energy_zcr_detector:
+            return -1, -1
+        return None
+
+    def _extract_all_batched(self, fname, starts: List[int], band) -> Dict[int, np.ndarray]:
+        """All windows of a raw-PCM reference in one VAD launch."""
+        if isinstance(fname, str):
+            pcm_all = np.memmap(fname, dtype="<i2", mode="r")
+        elif isinstance(fname, np.ndarray):
+            raw = np.ascontiguousarray(fname).view(np.uint8)
+            pcm_all = raw[: (len(raw) // 2) * 2].view("<i2")
+        else:
+            raw = np.frombuffer(fname, dtype=np.uint8)
+            pcm_all = raw[: (len(raw) // 2) * 2].view("<i2")
+        pieces, off = [], [0]
+        for s in starts:  # whole-second starts: every piece but a clipped last one keeps 16 B alignment
+            lo = min(len(pcm_all), int(round(s * self.frame_rate)))
+            hi = min(len(pcm_all), lo + int(round(self.segment_duration * self.frame_rate)))
+            pieces.append(np.asarray(pcm_all[lo:hi]))
+            off.append(off[-1] + (hi - lo))
+        out, out_off = _native.get_handle().vad_energy_zcr(
+            np.concatenate(pieces) if pieces else np.zeros(0, np.int16), off, self.frame_rate,
+            self.sample_rate, self._non_speech_label, DEFAULT_ENERGY_THRESHOLD, band[0], band[1])
+        return {s: out[out_off[i]:out_off[i + 1]].astype(np.float64) for i, s in enumerate(starts)}
+
+    def fit(self, fname, *_) -> "MultiSegmentVideoSpeechTransformer":
+        total_duration = self._probe_duration(fname)
+        starts = self._segment_starts(total_duration)
+        logger.info("multi-segment sync: sampling %d segment(s) of up to %ds at %s",
+                    len(starts), self.segment_duration, [int(s) for s in starts])
+        sparse = np.zeros(int(total_duration * self.sample_rate) + 2, dtype=float)
+
+        def place(start, seg_speech):
+            begin = int(start * self.sample_rate)
+            end = min(begin + len(seg_speech), len(sparse))
+            if end > begin:
+                sparse[begin:end] = seg_speech[: end - begin]
+
+        band = self._batched_params()
+        own_extract = type(self)._extract_segment_speech is MultiSegmentVideoSpeechTransformer._extract_segment_speech \
+            and "_extract_segment_speech" not in self.__dict__
+        if band is not None and own_extract and self._pcm_bytes_of(fname) is not None:
+            for start, seg_speech in self._extract_all_batched(fname, starts, band).items():
+                if len(seg_speech):
+                    place(start, seg_speech)
+        else:
+            workers = max(1, min(self.parallel_workers, len(starts)))
+            with ThreadPoolExecutor(max_workers=workers) as executor:
+                pending = {executor.submit(self._extract_segment_speech, fname, s): s for s in starts}
+                for fut in as_completed(pending):
+                    try:
+                        start, seg_speech = fut.result()
+                    except Exception as e:  # one bad window must not sink the sync (:878-882)
+                        logger.warning("failed to extract segment at %ds: %s", pending[fut], e)
+                        continue
+                    place(start, seg_speech)
+        if not np.any(sparse > 0):
+            raise ValueError("Unable to detect speech in any sampled segment. "
+                             "Perhaps try specifying a different stream / track, or a different vad.")
+        self.video_speech_results_ = sparse
         logger.info("total of speech segments: %s", np.sum(self.video_speech_results_))
         return self
 

@@ -287,6 +287,46 @@ def gen_maxscore(mods, out):
         out["maxscore_fail"] = str(e)
 
 
+def gen_segment_starts(mods, out):
+    """MultiSegmentVideoSpeechTransformer._segment_starts (speech_transformers.py:812-830) and the
+    sparse-signal assembly of .fit (:855-895) with a stubbed per-segment extractor."""
+    st = mods["speech_transformers"]
+    rows = []
+    for total in (40.0, 60.0, 61.0, 119.5, 120.0, 600.0, 900.0, 3600.25, 7200.0, 95.0, 150.0):
+        for count in (1, 3, 6, 8):
+            for dur in (10, 60):
+                for skip in (False, True):
+                    t = st.MultiSegmentVideoSpeechTransformer(
+                        vad="webrtc", sample_rate=100, frame_rate=48000, non_speech_label=0.0,
+                        segment_count=count, segment_duration=dur, skip_intro_outro=skip)
+                    rows.append({"total": total, "count": count, "duration": dur, "skip": skip,
+                                 "starts": [int(v) for v in t._segment_starts(total)]})
+    out["segment_starts"] = rows
+    # assembly: segment s returns the constant (s % 7 + 1) / 8 for dur seconds (last one clipped by
+    # the array end), one segment fails
+    asm = []
+    for total, count, dur in ((120.0, 3, 10), (325.37, 5, 30), (59.0, 4, 60)):
+        st.ffmpeg.probe = lambda *a, **k: {"format": {"duration": str(total)}}
+        t = st.MultiSegmentVideoSpeechTransformer(
+            vad="subs_then_webrtc", sample_rate=100, frame_rate=48000, non_speech_label=0.0,
+            segment_count=count, segment_duration=dur)
+        starts = t._segment_starts(total)
+        failing = starts[1] if len(starts) > 1 else None
+
+        def extract(fname, start, _dur=dur, _failing=failing):
+            if start == _failing:
+                raise RuntimeError("boom")
+            return start, np.full(_dur * 100, (start % 7 + 1) / 8.0)
+
+        t._extract_segment_speech = extract
+        t.fit("ref.mkv")
+        x = t.transform()
+        levels, rs, re = cases.run_lengths(x)
+        asm.append({"total": total, "count": count, "duration": dur, "vad": t.vad, "len": int(len(x)),
+                    "failing": failing, "runs": [[int(a), int(b), float(x[a])] for a, b in zip(rs, re)]})
+    out["segment_assembly"] = asm
+
+
 def gen_misc(mods, out):
     st = mods["speech_transformers"]
     mix = st.ComputeSpeechFrameBoundariesMixin()
@@ -307,6 +347,7 @@ def main():
     gen_raster(mods, out, srt)
     gen_gss(mods, out)
     gen_maxscore(mods, out)
+    gen_segment_starts(mods, out)
     gen_misc(mods, out)
     out["_meta"] = {"reference": "smacke/ffsubsync @ /root/reference (v0.5.0)",
                     "numpy": np.__version__, "python": sys.version.split()[0],

@@ -154,6 +154,52 @@ def test_video_speech_transformer_chunk_protocol(handle):
         VideoSpeechTransformer("energy", 100, fr, 0.0).fit(b"")
 
 
+def test_multi_segment_transformer_batched_vs_threads_vs_oracle(handle, tmp_path):
+    """MultiSegmentVideoSpeechTransformer on raw PCM: the one-launch batched path, the reference's
+    thread-pool path (one VideoSpeechTransformer per window, -ss/-t emulated on the raw PCM) and the
+    oracle VAD placed by hand must agree; the sparse signal then aligns like the full one."""
+    from ffsubsync_b200.speech_transformers import MultiSegmentVideoSpeechTransformer
+    fr, dur = 16000, 333.37
+    n_win = int(dur * 100)
+    cls = np.repeat(np.random.RandomState(21).randint(0, 2, n_win // 25 + 1), 25)[:n_win].astype(np.uint8)
+    pcm = vo.synth_pcm(cls, 160, seed=7)
+    pcm = np.concatenate([pcm, np.full(59, 9000, np.int16)])       # ragged tail (partial last window)
+    total = len(pcm) / fr
+    full = vo.energy_zcr_detect(pcm.tobytes(), 100, fr, 0.0)
+
+    def make(**kw):
+        return MultiSegmentVideoSpeechTransformer("energy_zcr", 100, fr, 0.0, segment_count=5,
+                                                  segment_duration=40, **kw)
+
+    batched = make().fit(pcm).transform()
+    want = np.zeros(int(total * 100) + 2)
+    t = make()
+    starts = t._segment_starts(total)
+    assert len(starts) == 5
+    for s in starts:
+        seg = vo.energy_zcr_detect(pcm[s * fr:(s + 40) * fr].tobytes(), 100, fr, 0.0)
+        end = min(s * 100 + len(seg), len(want))
+        want[s * 100:end] = seg[:end - s * 100]
+    assert np.array_equal(batched, want)
+    for s in starts:                                                # windows sit at their true positions
+        assert np.array_equal(batched[s * 100:s * 100 + 4000], full[s * 100:s * 100 + 4000])
+    # thread-pool path: instance-level extractor forces it; .pcm file source
+    path = str(tmp_path / "ref.pcm")
+    pcm.tofile(path)
+    t2 = make(parallel_workers=3)
+    t2._extract_segment_speech = lambda fname, start: MultiSegmentVideoSpeechTransformer._extract_segment_speech(t2, fname, start)
+    assert np.array_equal(t2.fit(path).transform(), want)
+    assert np.array_equal(make().fit(path).transform(), want)      # batched from the file (memmap)
+    fused = MultiSegmentVideoSpeechTransformer("fused:union", 100, fr, 0.0, segment_count=5,
+                                               segment_duration=40).fit(pcm).transform()
+    assert np.all((fused > 0) >= (want > 0)) and len(fused) == len(want)   # union with energy-only: superset
+    # the sparse reference recovers a planted shift like the full reference does
+    from ffsubsync_b200.aligners import FFTAligner
+    sub = np.concatenate([np.zeros(321), full])[:len(full)]
+    assert FFTAligner(6000).fit_transform(batched, sub) == -321
+    assert FFTAligner(6000).fit_transform(full, sub) == -321
+
+
 # ========================================================================= rasteriser (K2, K7)
 
 def test_raster_matches_reference_fixtures(handle, golden, gf):

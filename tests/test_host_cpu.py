@@ -204,3 +204,70 @@ def test_kernel_chain_emulation(built, R, S, o_t, W):
     bound = 2.0 ** -24 * np.sqrt(es * er)
     assert err <= 8 * bound + 1e-6, (err, bound)          # selection uses 64 * bound
     assert np.argmax(got) == np.argmax(want)
+
+
+# ---- MultiSegmentVideoSpeechTransformer host logic (reference tests/test_multi_segment.py:14-133) ----
+
+def _ms(**kw):
+    from ffsubsync_b200.speech_transformers import MultiSegmentVideoSpeechTransformer
+    args = dict(vad="energy", sample_rate=100, frame_rate=48000, non_speech_label=0.0, segment_duration=60)
+    args.update(kw)
+    return MultiSegmentVideoSpeechTransformer(**args)
+
+
+def test_multi_segment_starts_match_reference(golden):
+    for c in golden["segment_starts"]:
+        t = _ms(segment_count=c["count"], segment_duration=c["duration"], skip_intro_outro=c["skip"])
+        assert t._segment_starts(c["total"]) == c["starts"], c
+    # the reference's own assertions (tests/test_multi_segment.py:27-45)
+    t = _ms(segment_count=8)
+    starts = t._segment_starts(600.0)
+    assert len(starts) == 8 and starts == sorted(starts) and starts[0] == 0
+    assert all(0 <= s <= 600 - t.segment_duration for s in starts)
+    assert t._segment_starts(40.0) == [0]
+    t = _ms(segment_count=6, skip_intro_outro=True)
+    starts = t._segment_starts(900.0)
+    assert starts[0] >= t.START_MARGIN_SECONDS
+    assert starts[-1] <= 900 - t.END_MARGIN_SECONDS - t.segment_duration
+    assert _ms(vad="subs_then_webrtc").vad == "webrtc" and _ms(vad="fused:union").vad == "fused:union"
+
+
+def test_multi_segment_assembly_matches_reference(golden, monkeypatch):
+    for c in golden["segment_assembly"]:
+        t = _ms(vad="subs_then_webrtc", segment_count=c["count"], segment_duration=c["duration"])
+        assert t.vad == c["vad"]
+        monkeypatch.setattr(t, "_probe_duration", lambda fname, _t=c["total"]: _t)
+
+        def extract(fname, start, _c=c):
+            if start == _c["failing"]:
+                raise RuntimeError("boom")
+            return start, np.full(_c["duration"] * 100, (start % 7 + 1) / 8.0)
+
+        monkeypatch.setattr(t, "_extract_segment_speech", extract)
+        x = t.fit("ref.mkv").transform()
+        assert len(x) == c["len"]
+        want = np.zeros(c["len"])
+        for a, b, v in c["runs"]:
+            want[a:b] = v
+        assert np.array_equal(x, want)
+
+
+def test_multi_segment_errors(monkeypatch):
+    t = _ms(segment_count=3)
+    monkeypatch.setattr(t, "_probe_duration", lambda fname: 120.0)
+    monkeypatch.setattr(t, "_extract_segment_speech", lambda fname, start: (start, np.zeros(6000)))
+    with pytest.raises(ValueError, match="Unable to detect speech"):
+        t.fit("ref.mkv")
+    with pytest.raises(ValueError, match="multi-segment sync needs the reference duration"):
+        _ms().fit("/nonexistent/ref.mkv")
+
+
+def test_raw_pcm_window_follows_ss_t():
+    from ffsubsync_b200.speech_transformers import VideoSpeechTransformer
+    v = VideoSpeechTransformer("energy", 100, 16000, 0.0, start_seconds=3, max_duration_seconds=2)
+    assert v._pcm_window(16000 * 2 * 10) == (96000, 160000)
+    assert v._pcm_window(16000 * 2 * 4) == (96000, 128000)     # clipped by the end
+    assert v._pcm_window(1000) == (1000, 1000)                  # start past the end: empty
+    stream, total, _ = v._open_source((np.arange(16000 * 10) % 30000).astype(np.int16))
+    data = np.frombuffer(stream.read(1 << 30), np.int16)
+    assert total == 2.0 and len(data) == 32000 and data[0] == 18000

@@ -66,13 +66,14 @@ def main():
         torch.cuda.synchronize()
         return (time.perf_counter() - t0) / reps * 1e3
 
-    for ctas in ("2", "1"):
+    for stages, ctas in (("4", "2"), ("4", "1"), ("3", "1"), ("2", "1")):
+        os.environ["B2_VAD_STAGES"] = stages
         os.environ["B2_VAD_CTAS_FORCE"] = ctas
         tv = timed([vad])
         ta = timed([align])
         tb = timed([vad, align])
-        print("pairs=%d vad_ctas/SM=%s: vad alone %.3f ms, align alone %.3f ms, sum %.3f, both (2 streams) %.3f ms"
-              % (B, ctas, tv, ta, tv + ta, tb), flush=True)
+        print("pairs=%d vad stages=%s ctas/SM=%s: vad alone %.3f ms, align alone %.3f ms, sum %.3f, both (2 streams) %.3f ms"
+              % (B, stages, ctas, tv, ta, tv + ta, tb), flush=True)
 
 
 if __name__ == "__main__":
