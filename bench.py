@@ -242,9 +242,22 @@ def run_gpu(args):
                                              memspace=_native.B2_DEVICE), args.steps)
         stages = {"vad_ms": vad_ms, "rasterize_ms": ras_ms, "align_ms": ali_ms}
         achieved = BYTES_VAD * B / (vad_ms * 1e-3) / 1e9
+        # DRAM traffic per launch: ncu --set full capture of this kernel (profiles/r1j_ncu_summary.md,
+        # 16-pair launch): dram read+write = 3.7348 GB for 3.7325 GB of algorithmic bytes -> x1.0006
+        traffic_ratio = 1.0006
         roofline = {"kernel": "vad_energy_zcr_kernel", "bound": "hbm", "achieved": achieved, "peak": peak,
-                    "unit": "GB/s", "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+                    "unit": "GB/s", "frac": achieved / peak,
+                    "traffic": BYTES_VAD * B * traffic_ratio,
+                    "traffic_source": "ncu dram__bytes_read+write of a 16-pair launch (profiles/), scaled "
+                                      "by pairs; x%.4f of the algorithmic bytes" % traffic_ratio,
+                    "peak_source": peak_src,
+                    "frac_note": "the peak is a COPY bandwidth (read+write mix); this kernel is 98.8 % reads, "
+                                 "which HBM3e serves faster than a copy - frac > 1 is not an error. Against the "
+                                 "8000 GB/s data-sheet figure: %.3f" % (achieved / 8000.0),
                     "algorithmic_bytes_per_launch": BYTES_VAD * B,
+                    "stages_note": "stages_ms time b2_vad_energy_zcr / b2_rasterize / b2_align_batch called "
+                                   "one by one; the timed step calls b2_sync_batch, which replaces the float "
+                                   "rasteriser by bit masks (no rasterize_ms on that path)",
                     "whole_path": {"achieved": (BYTES_VAD + bytes_align(K)) * B * args.steps
                                    / (elapsed_ms * 1e-3) / 1e9 if world == 1 else None,
                                    "unit": "GB/s (algorithmic bytes of VAD + align over the step time)"}}

@@ -367,6 +367,15 @@ __global__ void __maxnreg__(kSubRegs)
   sub_correlate_body<true, true>(nullptr, jobs, spec, spec_energy, L, scores, job_energy, sub_bits);
 }
 
+// A/B variant (B2_SUB_REGS=128): same body, the whole register file (TMEM accumulators kept).
+__global__ void __launch_bounds__(kThreads, 1)
+    sub_correlate_bits_r128_kernel(const SubJob* __restrict__ jobs, const float4* __restrict__ spec,
+                                   const float* __restrict__ spec_energy, int L,
+                                   float* __restrict__ scores, float2* __restrict__ job_energy,
+                                   const uint32_t* __restrict__ sub_bits) {
+  sub_correlate_body<true, true>(nullptr, jobs, spec, spec_energy, L, scores, job_energy, sub_bits);
+}
+
 // A/B variant (B2_ACC=reg): accumulators in registers, 128 registers per thread.
 __global__ void __launch_bounds__(kThreads, 1)
     sub_correlate_regacc_kernel(const float* __restrict__ sub, const SubJob* __restrict__ jobs,
@@ -510,6 +519,18 @@ __global__ void __launch_bounds__(256) rescore_kernel(const SelJob* __restrict__
       // its value after x -> 2x-1 is (2*level - 1) inside a cue and -1 outside
       const uint32_t* bits = sub_bits + job.bits_off;
       const double hi = 2.0 * (double)job.sub_level - 1.0;
+      for (; i + 7 * 256 < a1; i += 8 * 256) {  // 16 independent loads in flight per thread
+        uint32_t bw[8];
+        float rv[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+          bw[u] = __ldg(bits + ((i + u * 256) >> 5));
+          rv[u] = __ldg(r + i + u * 256 + o);
+        }
+#pragma unroll
+        for (int u = 0; u < 8; ++u)  // 256 = 0 (mod 32): the bit position is the same for all u
+          acc = fma(((bw[u] >> (i & 31)) & 1u) ? hi : -1.0, 2.0 * (double)rv[u] - 1.0, acc);
+      }
       for (; i < a1; i += 256) {
         const double a = ((__ldg(bits + (i >> 5)) >> (i & 31)) & 1u) ? hi : -1.0;
         const double b = 2.0 * (double)__ldg(r + i + o) - 1.0;
@@ -687,7 +708,11 @@ int b2i_align_launch(b2_ctx* h, const float* d_ref, const int64_t* ref_off, cons
     B2_TRY(b2i_raster_bits_launch(h, cue_src, B, K, sub_off, bits_off.data(), d_bits));
     B2_CUDA(h, cudaFuncSetAttribute(sub_correlate_bits_kernel,
                                     cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytesBits));
+    B2_CUDA(h, cudaFuncSetAttribute(sub_correlate_bits_r128_kernel,
+                                    cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytesBits));
   }
+  const char* regs_env = getenv("B2_SUB_REGS");
+  const bool r128 = regs_env && atoi(regs_env) == 128;
 
   // score buffers + per-(pair,ratio) bookkeeping
   long long score_total = 0, energy_total = 0;
@@ -753,7 +778,10 @@ int b2i_align_launch(b2_ctx* h, const float* d_ref, const int64_t* ref_off, cons
                                                                     spec, spec_energy);
       B2_CHECK_LAUNCH(h, "ref_spectra_kernel");
     }
-    if (cue_mode)
+    if (cue_mode && r128)
+      sub_correlate_bits_r128_kernel<<<(unsigned)jobs.size(), kThreads, kSmemBytesBits, h->stream>>>(
+          d_jobs, spec, spec_energy, L, scores, job_energy, d_bits);
+    else if (cue_mode)
       sub_correlate_bits_kernel<<<(unsigned)jobs.size(), kThreads, kSmemBytesBits, h->stream>>>(
           d_jobs, spec, spec_energy, L, scores, job_energy, d_bits);
     else if (h->acc_in_tmem)
