@@ -251,7 +251,7 @@ def run_gpu(args):
                     "traffic_source": "ncu dram__bytes_read+write of a 16-pair launch (profiles/), scaled "
                                       "by pairs; x%.4f of the algorithmic bytes" % traffic_ratio,
                     "peak_source": peak_src,
-                    "frac_note": "the peak is a COPY bandwidth (read+write mix); this kernel is 98.8 % reads, "
+                    "frac_note": "the peak is a COPY bandwidth (read+write mix); this kernel is 98.8 %% reads, "
                                  "which HBM3e serves faster than a copy - frac > 1 is not an error. Against the "
                                  "8000 GB/s data-sheet figure: %.3f" % (achieved / 8000.0),
                     "algorithmic_bytes_per_launch": BYTES_VAD * B,
