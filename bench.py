@@ -175,7 +175,7 @@ def run_gpu(args):
 
     def step():
         bs.sync_device(pcm_d, pcm_off, pairs.cue_start, pairs.cue_end, pairs.cue_off, out=out)
-        if world > 1:  # the only exchange of the path: per-pair results to rank 0 (NCCL)
+        if world > 1 and not os.environ.get("B2_BENCH_NO_GATHER"):  # the only exchange of the path: per-pair results to rank 0 (NCCL); the env knob is a diagnostic
             packed[:, 0] = out["best_score"]
             packed[:, 1] = out["best_offset"].to(torch.float64)
             packed[:, 2] = out["best_k"].to(torch.float64)
@@ -192,8 +192,7 @@ def run_gpu(args):
     if world > 1:
         torch.distributed.barrier()
     torch.cuda.synchronize()
-    if rank == 0:
-        sampler.start()
+    sampler.start()
     launches0 = h.launch_count
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     ev0.record(stream)
@@ -203,9 +202,18 @@ def run_gpu(args):
     torch.cuda.synchronize()
     if world > 1:
         torch.distributed.barrier()
-    elapsed_ms = distributed.max_over_ranks(ev0.elapsed_time(ev1), dev)
+    local_ms = ev0.elapsed_time(ev1)
+    elapsed_ms = distributed.max_over_ranks(local_ms, dev)
     launches = h.launch_count - launches0
-    clocks = sampler.stop() if rank == 0 else None
+    clocks = sampler.stop()
+    per_rank = None
+    if world > 1:  # every rank's own device time and SM clock, for the record
+        mine = torch.tensor([local_ms / args.steps, float(clocks.get("sm_mhz") or 0.0)], dtype=torch.float64,
+                            device=dev)
+        allr = torch.empty((world, 2), dtype=torch.float64, device=dev)
+        torch.distributed.all_gather_into_tensor(allr, mine)
+        per_rank = {"ms_per_step": [round(v, 4) for v in allr[:, 0].tolist()],
+                    "sm_mhz": allr[:, 1].tolist()}
 
     # ---- per-stage device times (CUDA events on the launching stream), rank 0 only -------------
     stages, roofline, e2e, cpu_base = {}, None, None, None
@@ -308,7 +316,7 @@ def run_gpu(args):
                        "signal_frames": 720000, "pcm_samples_per_pair": 115200000,
                        "l2_policy": "inputs (%.1f GB PCM per GPU) are far larger than the 126 MB L2"
                                     % (B * 0.2304), "parallelism": "pairs block-sharded, dp%d" % world},
-            "verified_offsets": ok, "gpu_launches": int(launches), "clocks": clocks, "stages_ms": stages,
+            "verified_offsets": ok, "gpu_launches": int(launches), "clocks": clocks, "per_rank": per_rank, "stages_ms": stages,
             "roofline": roofline, "e2e": e2e, "cpu_baseline": cpu_base,
         }
         print(json.dumps(line))
