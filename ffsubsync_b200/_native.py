@@ -24,7 +24,8 @@ EXPORTS = [
     "b2_version", "b2_create", "b2_destroy", "b2_set_stream", "b2_synchronize", "b2_last_error",
     "b2_launch_count", "b2_vad_frames_per_window", "b2_vad_num_windows", "b2_vad_energy_zcr",
     "b2_rasterize_lengths", "b2_rasterize", "b2_blend_signals", "b2_first_last_nonzero", "b2_align_batch",
-    "b2_reduce_ratios", "b2_sync_batch", "b2_synth_pcm",
+    "b2_reduce_ratios", "b2_sync_batch", "b2_synth_pcm", "b2_vad_stream_begin", "b2_vad_stream_push",
+    "b2_vad_stream_windows", "b2_vad_stream_end",
 ]
 
 
@@ -81,6 +82,12 @@ def load() -> ctypes.CDLL:
                                       _i64, ctypes.c_int, ctypes.c_int, _vp, _vp, _vp, _vp, _vp,
                                       ctypes.c_int, _f64, _i32, _vp, _vp, _vp, _vp, _vp, ctypes.c_int]
         lib.b2_synth_pcm.argtypes = [_vp, _vp, _i64, ctypes.c_int, ctypes.c_uint32, _vp, ctypes.c_int]
+        lib.b2_vad_stream_begin.argtypes = [_vp, ctypes.c_int, ctypes.c_int, _f32, _i64, ctypes.c_int,
+                                            ctypes.c_int]
+        lib.b2_vad_stream_push.argtypes = [_vp, _vp, _i64]
+        lib.b2_vad_stream_windows.argtypes = [_vp]
+        lib.b2_vad_stream_windows.restype = _i64
+        lib.b2_vad_stream_end.argtypes = [_vp, _vp, _i64, ctypes.POINTER(_i64)]
         _lib = lib
         return lib
 
@@ -164,6 +171,31 @@ class Handle:
                                         int(z_hi), _ptr(out), _ptr(out_off), memspace)
         self._check(st, "b2_vad_energy_zcr")
         return out, out_off
+
+    # streaming detector (b2_vad_stream_*): push() returns before the chunk is processed
+    def vad_stream_begin(self, frame_rate: int, sample_rate: int, non_speech_label: float,
+                         energy_threshold: int, z_lo: int = -1, z_hi: int = -1) -> None:
+        self._check(self.lib.b2_vad_stream_begin(self.h, frame_rate, sample_rate, float(non_speech_label),
+                                                 int(energy_threshold), int(z_lo), int(z_hi)),
+                    "b2_vad_stream_begin")
+
+    def vad_stream_push(self, chunk) -> None:
+        """chunk: bytes-like or uint8/int16 array (host); copied before the call returns."""
+        if isinstance(chunk, np.ndarray):
+            buf = np.ascontiguousarray(chunk)
+            ptr, n = buf.ctypes.data, buf.nbytes
+        else:
+            buf = np.frombuffer(chunk, dtype=np.uint8)
+            ptr, n = (buf.ctypes.data if len(buf) else None), len(buf)
+        self._check(self.lib.b2_vad_stream_push(self.h, ptr, n), "b2_vad_stream_push")
+
+    def vad_stream_end(self) -> np.ndarray:
+        n = int(self.lib.b2_vad_stream_windows(self.h))
+        out = np.empty(max(n, 0), dtype=np.float32)
+        got = _i64(0)
+        self._check(self.lib.b2_vad_stream_end(self.h, _ptr(out) if n > 0 else None, max(n, 0),
+                                               ctypes.byref(got)), "b2_vad_stream_end")
+        return out[: got.value]
 
     def synth_pcm(self, window_class, n_windows: int, fpw: int, seed: int, out=None,
                   memspace: int = B2_HOST):

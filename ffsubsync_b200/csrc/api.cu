@@ -67,6 +67,13 @@ extern "C" int b2_destroy(b2_handle h) {
     if (w.p) cudaFree(w.p);
   for (auto& p : h->pinned)
     if (p.p) cudaFreeHost(p.p);
+  for (auto& sl : h->vs.slot) {
+    if (sl.hp) cudaFreeHost(sl.hp);
+    if (sl.hout) cudaFreeHost(sl.hout);
+    if (sl.dp) cudaFree(sl.dp);
+    if (sl.dout) cudaFree(sl.dout);
+    if (sl.ev) cudaEventDestroy(sl.ev);
+  }
   if (h->stream2) cudaStreamSynchronize(h->stream2);
   for (auto& ring : h->meta)
     for (auto& m : ring) {
@@ -300,6 +307,104 @@ extern "C" int b2_vad_energy_zcr(b2_handle h, const int16_t* pcm, const int64_t*
     B2_TRY(copy_out(h, out, d_out, (size_t)w_total * 4));
     B2_CUDA(h, cudaStreamSynchronize(h->stream));
   }
+  return B2_OK;
+}
+
+// ---- streaming VAD (chunk loop of speech_transformers.py:710-746) -----------------------------
+static int vs_collect(b2_ctx* h, b2_ctx::VadStream::Slot& sl) {
+  if (!sl.busy) return B2_OK;
+  B2_CUDA(h, cudaEventSynchronize(sl.ev));
+  h->vs.results.insert(h->vs.results.end(), sl.hout, sl.hout + sl.n_out);
+  sl.busy = false;
+  return B2_OK;
+}
+
+extern "C" int b2_vad_stream_begin(b2_handle h, int frame_rate, int sample_rate, float non_speech_label,
+                                   int64_t energy_threshold, int z_lo, int z_hi) {
+  B2_ENTER(h);
+  auto& vs = h->vs;
+  if (vs.active) B2_FAIL(h, B2_ERR_BAD_ARG, "vad stream: already open on this handle");
+  const int fpw = b2_vad_frames_per_window(frame_rate, sample_rate);
+  if (fpw <= 0) B2_FAIL(h, B2_ERR_BAD_ARG, "vad stream: bad frame_rate/sample_rate");
+  if (energy_threshold < 0) B2_FAIL(h, B2_ERR_BAD_ARG, "vad stream: negative energy threshold");
+  vs.frame_rate = frame_rate;
+  vs.sample_rate = sample_rate;
+  vs.fpw = fpw;
+  vs.label = non_speech_label;
+  vs.thr = energy_threshold;
+  vs.z_lo = z_lo < 0 ? 0 : z_lo;
+  vs.z_hi = z_hi < 0 ? (3 * fpw) / 8 : z_hi;
+  vs.windows = 0;
+  vs.seq = 0;
+  vs.results.clear();
+  vs.active = true;
+  return B2_OK;
+}
+
+extern "C" int b2_vad_stream_push(b2_handle h, const void* pcm_bytes, int64_t n_bytes) {
+  B2_ENTER(h);
+  auto& vs = h->vs;
+  if (!vs.active) B2_FAIL(h, B2_ERR_BAD_ARG, "vad stream: not open");
+  if (n_bytes < 0 || (n_bytes && !pcm_bytes)) B2_FAIL(h, B2_ERR_BAD_ARG, "vad stream: bad chunk");
+  const int64_t n = n_bytes / 2;  // an odd trailing byte is ignored (speech_transformers.py:745)
+  if (n == 0) return B2_OK;
+  const int64_t nwin = (n + vs.fpw - 1) / vs.fpw;
+  auto& sl = vs.slot[vs.seq % b2_ctx::VadStream::kSlots];
+  B2_TRY(vs_collect(h, sl));  // the slot's previous chunk (kSlots pushes ago) must be done
+  if ((size_t)n * 2 > sl.cap) {
+    if (sl.hp) B2_CUDA(h, cudaFreeHost(sl.hp));
+    if (sl.dp) B2_CUDA(h, cudaFree(sl.dp));
+    sl.hp = sl.dp = nullptr;
+    sl.cap = 0;
+    const size_t want = (size_t)n * 2 + 256;
+    B2_CUDA(h, cudaMallocHost(&sl.hp, want));
+    B2_CUDA(h, cudaMalloc(&sl.dp, want));
+    sl.cap = want;
+  }
+  if ((size_t)nwin * 4 > sl.out_cap) {
+    if (sl.hout) B2_CUDA(h, cudaFreeHost(sl.hout));
+    if (sl.dout) B2_CUDA(h, cudaFree(sl.dout));
+    sl.hout = sl.dout = nullptr;
+    sl.out_cap = 0;
+    const size_t want = (size_t)nwin * 4 + 256;
+    B2_CUDA(h, cudaMallocHost((void**)&sl.hout, want));
+    B2_CUDA(h, cudaMalloc((void**)&sl.dout, want));
+    sl.out_cap = want;
+  }
+  if (!sl.ev) B2_CUDA(h, cudaEventCreateWithFlags(&sl.ev, cudaEventDisableTiming));
+  memcpy(sl.hp, pcm_bytes, (size_t)n * 2);
+  B2_CUDA(h, cudaMemcpyAsync(sl.dp, sl.hp, (size_t)n * 2, cudaMemcpyHostToDevice, h->stream));
+  const int64_t pcm_off[2] = {0, n}, out_off[2] = {0, nwin};
+  B2_TRY(b2i_vad_launch(h, (const int16_t*)sl.dp, pcm_off, 1, vs.fpw, vs.label, vs.thr, vs.z_lo, vs.z_hi,
+                        sl.dout, out_off));
+  B2_CUDA(h, cudaMemcpyAsync(sl.hout, sl.dout, (size_t)nwin * 4, cudaMemcpyDeviceToHost, h->stream));
+  B2_CUDA(h, cudaEventRecord(sl.ev, h->stream));
+  sl.n_out = nwin;
+  sl.busy = true;
+  vs.windows += nwin;
+  ++vs.seq;
+  return B2_OK;
+}
+
+extern "C" int64_t b2_vad_stream_windows(b2_handle h) { return (h && h->vs.active) ? h->vs.windows : -1; }
+
+extern "C" int b2_vad_stream_end(b2_handle h, float* out, int64_t capacity, int64_t* n_out) {
+  B2_ENTER(h);
+  auto& vs = h->vs;
+  if (!vs.active) B2_FAIL(h, B2_ERR_BAD_ARG, "vad stream: not open");
+  const int ns = b2_ctx::VadStream::kSlots;
+  for (uint64_t i = vs.seq > (uint64_t)ns ? vs.seq - ns : 0; i < vs.seq; ++i)  // oldest first
+    B2_TRY(vs_collect(h, vs.slot[i % ns]));
+  vs.active = false;
+  const int64_t total = (int64_t)vs.results.size();
+  if (n_out) *n_out = total;
+  if (total > capacity || (total && !out)) {
+    vs.results.clear();
+    B2_FAIL(h, B2_ERR_BAD_ARG, "vad stream: output holds %lld windows, capacity %lld", (long long)total,
+            (long long)capacity);
+  }
+  if (total) memcpy(out, vs.results.data(), (size_t)total * 4);
+  vs.results.clear();
   return B2_OK;
 }
 

@@ -51,6 +51,27 @@ struct b2_ctx {
   int ring = 0;                    // ring in use: 0 = caller-facing stream, 1 = internal stream2
   // b2_sync_batch overlaps the VAD of sub-batch i+1 (stream) with the alignment of sub-batch i
   // (stream2); events from a small pool order the two
+  // b2_vad_stream_*: ring of pinned/device chunk buffers (H2D + kernel + D2H of chunk i in flight
+  // while the caller produces chunk i+1)
+  struct VadStream {
+    static const int kSlots = 3;
+    struct Slot {
+      void* hp = nullptr;     // pinned PCM
+      void* dp = nullptr;     // device PCM
+      float* hout = nullptr;  // pinned windows
+      float* dout = nullptr;  // device windows
+      size_t cap = 0, out_cap = 0;
+      cudaEvent_t ev = nullptr;
+      int64_t n_out = 0;
+      bool busy = false;
+    } slot[kSlots];
+    bool active = false;
+    int frame_rate = 0, sample_rate = 0, fpw = 0, z_lo = 0, z_hi = 0;
+    float label = 0.f;
+    int64_t thr = 0, windows = 0;
+    uint64_t seq = 0;
+    std::vector<float> results;
+  } vs;
   cudaStream_t stream2 = nullptr;
   static const int kEvents = 16;
   cudaEvent_t ev_pool[kEvents] = {};

@@ -85,6 +85,15 @@ def _make_energy_zcr_detector(
             -1 if z_lo is None else z_lo, -1 if z_hi is None else z_hi)
         return out.astype(np.float64)
 
+    # streaming form for the chunk loop (b2_vad_stream_*): same windows as one _detect call per
+    # chunk, but push() only enqueues copy + kernel, so reading / decoding the next chunk overlaps
+    def _stream_begin():
+        _native.get_handle().vad_stream_begin(frame_rate, sample_rate, non_speech_label, energy_threshold,
+                                              -1 if z_lo is None else z_lo, -1 if z_hi is None else z_hi)
+
+    _detect.stream_begin = _stream_begin
+    _detect.stream_push = lambda chunk: _native.get_handle().vad_stream_push(chunk)
+    _detect.stream_end = lambda: _native.get_handle().vad_stream_end().astype(np.float64)
     return _detect
 
 
@@ -275,6 +284,10 @@ class VideoSpeechTransformer(TransformerMixin):
         if self.max_duration_seconds is not None and total_duration is not None:
             total_duration = min(total_duration, self.max_duration_seconds)
         media_bstring: List[np.ndarray] = []
+        # detectors that expose the streaming protocol (this package's energy detectors) take the
+        # chunks without a device synchronisation per chunk; anything else is called per chunk
+        streaming = all(hasattr(detector, a) for a in ("stream_begin", "stream_push", "stream_end"))
+        pushed = 0
         bytes_per_frame = 2
         bytes_per_window = bytes_per_frame * self.frame_rate // self.sample_rate
         windows_per_buffer = 10000
@@ -296,10 +309,18 @@ class VideoSpeechTransformer(TransformerMixin):
                         logger.warning("progress_handler raised: %s", e)
                 if self.vlc_mode and total_duration is not None:
                     print("%d" % int(simple_progress * 100.0 / total_duration), flush=True)
-                media_bstring.append(detector(np.frombuffer(in_bytes, np.uint8)))
+                if streaming:
+                    if pushed == 0:
+                        detector.stream_begin()
+                    detector.stream_push(in_bytes)
+                    pushed += 1
+                else:
+                    media_bstring.append(detector(np.frombuffer(in_bytes, np.uint8)))
         finally:
             if closer is not None:
                 closer()
+            if streaming and pushed:
+                media_bstring.append(detector.stream_end())
         if len(media_bstring) == 0:
             raise ValueError(
                 "Unable to detect speech. "

@@ -78,6 +78,21 @@ int b2_vad_energy_zcr(b2_handle h, const int16_t* pcm, const int64_t* pcm_off, i
                       int64_t energy_threshold, int z_lo, int z_hi,
                       float* out, const int64_t* out_off, int memspace);
 
+/* Streaming form of the same detector for the reference's chunk loop
+ * (ffsubsync/speech_transformers.py:710-746: read <= 100 s of ffmpeg's pipe, detect, append):
+ * b2_vad_stream_push copies the HOST chunk into a pinned ring slot, enqueues H2D copy + kernel +
+ * D2H of the chunk's windows and returns without synchronising, so decoding chunk i+1 overlaps
+ * the transfer and detection of chunk i.  Every chunk is detected on its own exactly like one
+ * detector call (ceil(n/fpw) windows, a partial last window is non-speech; an odd trailing byte is
+ * ignored).  b2_vad_stream_end waits, writes all windows in push order to HOST out
+ * (capacity in floats, B2_ERR_BAD_ARG when too small) and closes the stream.
+ * b2_vad_stream_windows = windows pushed so far (what `out` must hold). */
+int b2_vad_stream_begin(b2_handle h, int frame_rate, int sample_rate, float non_speech_label,
+                        int64_t energy_threshold, int z_lo, int z_hi);
+int b2_vad_stream_push(b2_handle h, const void* pcm_bytes, int64_t n_bytes);
+int64_t b2_vad_stream_windows(b2_handle h);
+int b2_vad_stream_end(b2_handle h, float* out, int64_t capacity, int64_t* n_out);
+
 /* ---- subtitle side: replaces SubtitleScaler.fit + SubtitleSpeechTransformer.fit ----------
  * ffsubsync/subtitle_transformers.py:35-47 and ffsubsync/speech_transformers.py:957-980.
  * Cues (seconds, float64, unscaled) of pair b are [cue_off[b], cue_off[b+1]); keep[i]==0 for

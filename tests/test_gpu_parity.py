@@ -154,6 +154,39 @@ def test_video_speech_transformer_chunk_protocol(handle):
         VideoSpeechTransformer("energy", 100, fr, 0.0).fit(b"")
 
 
+def test_vad_stream_matches_per_chunk_detection(handle):
+    """b2_vad_stream_*: every pushed chunk is detected like one detector call (ceil(n/fpw) windows,
+    partial last window non-speech, odd trailing byte dropped); the ring (3 slots) wraps, chunk
+    sizes change, results come back in push order."""
+    from ffsubsync_b200 import _native
+    fr, fpw = 16000, 160
+    cls = np.random.RandomState(31).randint(0, 3, 9000).astype(np.uint8)
+    raw = vo.synth_pcm(cls, fpw, seed=3).tobytes()
+    sizes = [320 * 700, 320 * 700 + 1, 7, 0, 320 * 2100 + 38, 320, 320 * 1500 - 5, 2, 320 * 900, 1]
+    chunks, pos = [], 0
+    for n in sizes:
+        chunks.append(raw[pos:pos + n])
+        pos += n
+    chunks.append(raw[pos:])
+    want = np.concatenate([vo.energy_zcr_detect(c[:len(c) // 2 * 2], 100, fr, 0.25) for c in chunks if len(c) >= 2])
+    handle.vad_stream_begin(fr, 100, 0.25, 100000)
+    with pytest.raises(_native.NativeError, match="already open"):
+        handle.vad_stream_begin(fr, 100, 0.25, 100000)
+    for i, c in enumerate(chunks):
+        handle.vad_stream_push(np.frombuffer(c, np.uint8) if i % 2 else c)
+    got = handle.vad_stream_end()
+    assert got.dtype == np.float32 and np.array_equal(got.astype(np.float64), want)
+    with pytest.raises(_native.NativeError, match="not open"):
+        handle.vad_stream_push(b"\0\0")
+    handle.vad_stream_begin(fr, 100, 0.0, 100000)        # empty stream, and a second use of the handle
+    assert len(handle.vad_stream_end()) == 0
+    # band parameters are honoured (energy-only variant)
+    handle.vad_stream_begin(fr, 100, 0.0, 100000, 0, fpw)
+    handle.vad_stream_push(raw)
+    assert np.array_equal(handle.vad_stream_end().astype(np.float64),
+                          vo.energy_zcr_detect(raw, 100, fr, 0.0, 100000, 0, fpw))
+
+
 def test_multi_segment_transformer_batched_vs_threads_vs_oracle(handle, tmp_path):
     """MultiSegmentVideoSpeechTransformer on raw PCM: the one-launch batched path, the reference's
     thread-pool path (one VideoSpeechTransformer per window, -ss/-t emulated on the raw PCM) and the
