@@ -27,13 +27,13 @@ struct RasterParams {
   const double* levels;       // same shape as ratios, or null (= min(1/ratio, 1))
   const long long* out_off;   // [B*K+1]
   float* out;
-  int B, K, per_pair, sample_rate;
+  int B, K, per_pair, sample_rate, sig_base;
   double start_seconds;
 };
 
 // one warp per cue, grid.y = signal (b*K + k)
 __global__ void __launch_bounds__(256) raster_cues_kernel(RasterParams p) {
-  const int sig = blockIdx.y;
+  const int sig = blockIdx.y + p.sig_base;
   const int b = sig / p.K;
   const double ratio = p.per_pair ? p.ratios[sig] : p.ratios[sig - b * p.K];
   const long long c0 = p.cue_off[b], c1 = p.cue_off[b + 1];
@@ -65,12 +65,12 @@ struct RasterBitsParams {
   const long long* sig_off;    // [B*K+1]: only the differences (signal lengths) are used
   const long long* bits_off;   // [B*K+1] words
   uint32_t* bits;              // zeroed by the caller
-  int K, sample_rate;
+  int K, sample_rate, sig_base;  // blockIdx.y + sig_base = signal (grid.y is limited to 65535)
   double start_seconds;
 };
 
 __global__ void __launch_bounds__(256) raster_bits_kernel(RasterBitsParams p) {
-  const int sig = blockIdx.y;
+  const int sig = blockIdx.y + p.sig_base;
   const int b = sig / p.K;
   const double ratio = p.ratios[sig - b * p.K];
   const long long c0 = p.cue_off[b], c1 = p.cue_off[b + 1];
@@ -217,10 +217,12 @@ int b2i_raster_launch(b2_ctx* h, const double* cue_start, const double* cue_end,
   int64_t max_cues = 0;
   for (int b = 0; b < B; ++b) max_cues = std::max<int64_t>(max_cues, cue_off[b + 1] - cue_off[b]);
   if (max_cues == 0 || J == 0) return B2_OK;
-  if (J > 65535) B2_FAIL(h, B2_ERR_UNSUPPORTED, "rasterize: B*K > 65535 in one call");
-  dim3 grid((unsigned)std::min<int64_t>((max_cues + 7) / 8, 64), (unsigned)J);
-  raster_cues_kernel<<<grid, 256, 0, h->stream>>>(p);
-  B2_CHECK_LAUNCH(h, "raster_cues_kernel");
+  for (size_t j0 = 0; j0 < J; j0 += 65535) {
+    p.sig_base = (int)j0;
+    dim3 grid((unsigned)std::min<int64_t>((max_cues + 7) / 8, 64), (unsigned)std::min<size_t>(J - j0, 65535));
+    raster_cues_kernel<<<grid, 256, 0, h->stream>>>(p);
+    B2_CHECK_LAUNCH(h, "raster_cues_kernel");
+  }
   return B2_OK;
 }
 
@@ -233,7 +235,6 @@ int b2i_raster_bits_launch(b2_ctx* h, const B2CueSource* src, int B, int K, cons
   int64_t max_cues = 0;
   for (int b = 0; b < B; ++b) max_cues = std::max<int64_t>(max_cues, src->cue_off[b + 1] - src->cue_off[b]);
   if (max_cues == 0 || J == 0) return B2_OK;
-  if (J > 65535) B2_FAIL(h, B2_ERR_UNSUPPORTED, "rasterize: B*K > 65535 in one call");
   MetaArena a;
   B2_TRY(b2i_meta_begin(h, &a, nc * 17 + (B + 1) * 8 + (J + 1) * 16 + (size_t)K * 8 + 1024));
   RasterBitsParams p;
@@ -249,9 +250,12 @@ int b2i_raster_bits_launch(b2_ctx* h, const B2CueSource* src, int B, int K, cons
   p.K = K;
   p.sample_rate = src->sample_rate;
   p.start_seconds = src->start_seconds;
-  dim3 grid((unsigned)std::min<int64_t>((max_cues + 255) / 256, 64), (unsigned)J);
-  raster_bits_kernel<<<grid, 256, 0, h->stream>>>(p);
-  B2_CHECK_LAUNCH(h, "raster_bits_kernel");
+  for (size_t j0 = 0; j0 < J; j0 += 65535) {
+    p.sig_base = (int)j0;
+    dim3 grid((unsigned)std::min<int64_t>((max_cues + 255) / 256, 64), (unsigned)std::min<size_t>(J - j0, 65535));
+    raster_bits_kernel<<<grid, 256, 0, h->stream>>>(p);
+    B2_CHECK_LAUNCH(h, "raster_bits_kernel");
+  }
   return B2_OK;
 }
 

@@ -154,6 +154,41 @@ def test_video_speech_transformer_chunk_protocol(handle):
         VideoSpeechTransformer("energy", 100, fr, 0.0).fit(b"")
 
 
+def test_more_than_65535_signals_in_one_call(handle):
+    """The rasterisers index signals with grid.y (limit 65 535): larger batches are split into
+    several launches.  66 000 one-cue signals through b2_rasterize, and 33 000 pairs x 2 ratios
+    through b2_sync_batch (bit-mask path), spot-checked against the oracle."""
+    rs = np.random.RandomState(4)
+    J = 66000
+    st = rs.uniform(0.0, 0.5, J)
+    en = st + rs.uniform(0.05, 0.4, J)
+    out, off = handle.rasterize(st, en, None, np.arange(J + 1), [1.0], 1, False, 100, 0.0)
+    for j in list(range(0, J, 1777)) + [65534, 65535, 65536, J - 1]:
+        want = ro.rasterize(st[j:j + 1], en[j:j + 1], None, 100, 0, 1.0)[0]
+        assert np.array_equal(out[off[j]:off[j + 1]].astype(np.float64), want), j
+    B, fpw, nwin = 33000, 160, 12
+    cls = np.zeros(B * nwin, np.uint8)
+    delta = rs.randint(0, 4, B)
+    for b in range(B):                                   # speech windows [3+d, 7+d) of 12
+        cls[b * nwin + 3 + delta[b]: b * nwin + 7 + delta[b]] = 1
+    pcm = handle.synth_pcm(cls, len(cls), fpw, 3)
+    cs, ce = np.full(B, 0.03), np.full(B, 0.07)          # subtitle speech frames [3, 7)
+    ratios = [1.0, 0.5]
+    bs, bo, bk, a_s, a_o = handle.sync_batch(pcm, np.arange(B + 1) * nwin * fpw, 16000, 100, 0.0, 100000,
+                                             -1, -1, cs, ce, None, np.arange(B + 1), ratios, 0.0, 8,
+                                             want_all=True)
+    for b in list(range(0, B, 997)) + [32767, 32768, B - 1]:
+        ref_sig = vo.energy_zcr_detect(pcm[b * nwin * fpw:(b + 1) * nwin * fpw], 100, 16000, 0.0)
+        # tiny signals tie exactly at several offsets: the oracle's exact-arithmetic argmax is the
+        # defined answer (DESIGN.md section 2)
+        results = [ao.exact_align(ref_sig, ro.rasterize(cs[b:b + 1], ce[b:b + 1], None, 100, 0, r)[0], 8)
+                   for r in ratios]
+        wk = ao.max_score_select(results, 8)
+        assert (bk[b], bo[b]) == (wk, results[wk][1]), b
+        assert [int(a_o[2 * b]), int(a_o[2 * b + 1])] == [results[0][1], results[1][1]]
+        assert _score_ok(bs[b], results[wk][0])
+
+
 def test_vad_stream_matches_per_chunk_detection(handle):
     """b2_vad_stream_*: every pushed chunk is detected like one detector call (ceil(n/fpw) windows,
     partial last window non-speech, odd trailing byte dropped); the ring (3 slots) wraps, chunk
