@@ -54,6 +54,7 @@ struct SelJob {        // one (pair, ratio)
   int R, S, o_first;   // offset of scores[score_off]
   int m_lo, m_hi;      // valid window of m (inclusive); m_lo > m_hi: nothing survives
   int energy_slot, n_tiles;
+  int n_split;         // partial score arrays per tile (small batches split the block range over CTAs)
   int out_index;       // b*K + k
   int kind;            // 0 normal, 1 empty input, 2 everything masked
   int masked_offset;   // offset reported when kind == 2
@@ -391,9 +392,9 @@ __global__ void __launch_bounds__(kThreads, 1)
 // lowest index = largest offset among equal values), at most kCandMax of them.
 // Phase 1: fp32 maximum of the surviving window and the round-off bound tau, per (pair, ratio).
 __global__ void __launch_bounds__(256) window_max_kernel(const SelJob* __restrict__ jobs,
-                                                          const float* __restrict__ scores,
+                                                          float* __restrict__ scores,
                                                           const float2* __restrict__ job_energy,
-                                                          float2* __restrict__ job_stat) {
+                                                          float2* __restrict__ job_stat, int wt) {
   const SelJob job = jobs[blockIdx.x];
   const int tid = threadIdx.x;
   __shared__ float smax[256];
@@ -401,7 +402,16 @@ __global__ void __launch_bounds__(256) window_max_kernel(const SelJob* __restric
     if (tid == 0) job_stat[blockIdx.x] = make_float2(-INFINITY, 0.f);
     return;
   }
-  const float* c = scores + job.score_off;
+  float* c = scores + job.score_off;
+  if (job.n_split > 1) {  // add the partial score arrays (fixed order: deterministic) into the first
+    const int n = job.n_tiles * wt;
+    for (int m = tid; m < n; m += 256) {
+      float v = c[m];
+      for (int sp = 1; sp < job.n_split; ++sp) v += c[(size_t)sp * n + m];
+      c[m] = v;
+    }
+    __syncthreads();
+  }
   float mx = -INFINITY;
   for (int m = job.m_lo + tid; m <= job.m_hi; m += 256) mx = fmaxf(mx, c[m]);
   smax[tid] = mx;
@@ -413,8 +423,13 @@ __global__ void __launch_bounds__(256) window_max_kernel(const SelJob* __restric
   if (tid == 0) {
     float e2 = 0.f;
     for (int i = 0; i < job.n_tiles; ++i) {
-      const float2 e = job_energy[job.energy_slot + i];
-      e2 = fmaxf(e2, e.x * e.y);
+      float ex = 0.f, ey = 0.f;  // energies add over the chunks of a tile (Cauchy-Schwarz bound)
+      for (int sp = 0; sp < job.n_split; ++sp) {
+        const float2 e = job_energy[job.energy_slot + i * job.n_split + sp];
+        ex += e.x;
+        ey += e.y;
+      }
+      e2 = fmaxf(e2, ex * ey);
     }
     job_stat[blockIdx.x] = make_float2(smax[0], kTauRel * sqrtf(e2) + 1e-30f);
   }
@@ -715,10 +730,30 @@ int b2i_align_launch(b2_ctx* h, const float* d_ref, const int64_t* ref_off, cons
   const bool r128 = regs_env && atoi(regs_env) == 128;
 
   // score buffers + per-(pair,ratio) bookkeeping
-  long long score_total = 0, energy_total = 0;
+  // Small batches: with fewer (pair, ratio, tile) jobs than SMs the block loop of a job (35 blocks
+  // for a 2 h signal) would run on a handful of SMs.  The block range of every job is then cut into
+  // n_split chunks, each CTA inverse-transforms its own partial accumulator (the inverse FFT is
+  // linear) into its own partial score array, and window_max_kernel adds the partial arrays in a
+  // fixed order.  Costs one extra inverse transform per chunk, so chunks keep >= 4 blocks.
+  long long n_jobs_total = 0, max_blocks = 1;
   for (int b = 0; b < B; ++b) {
     PairPlan& p = pp[b];
     p.n_tiles = p.any ? (int)ceil_div64(p.o_max - p.o_min + 1, Wt) : 0;
+    for (int k = 0; k < K; ++k) {
+      const SelJob& s = sel[(size_t)b * K + k];
+      if (s.kind != 0) continue;
+      n_jobs_total += p.n_tiles;
+      max_blocks = std::max<long long>(max_blocks, ceil_div64(s.S, L));
+    }
+  }
+  int n_split = 1;
+  if (n_jobs_total > 0 && n_jobs_total < 2LL * h->sm_count)
+    n_split = (int)std::max<long long>(1, std::min<long long>(ceil_div64(2LL * h->sm_count, n_jobs_total),
+                                                               max_blocks / 4));
+  if (const char* e = getenv("B2_ALIGN_SPLIT")) n_split = std::max(1, atoi(e));  // test / tuning knob
+  long long score_total = 0, energy_total = 0;
+  for (int b = 0; b < B; ++b) {
+    PairPlan& p = pp[b];
     for (int k = 0; k < K; ++k) {
       SelJob& s = sel[(size_t)b * K + k];
       if (s.kind != 0) continue;
@@ -728,8 +763,9 @@ int b2i_align_launch(b2_ctx* h, const float* d_ref, const int64_t* ref_off, cons
       s.score_off = score_total;
       s.energy_slot = (int)energy_total;
       s.n_tiles = p.n_tiles;
-      score_total += (long long)p.n_tiles * Wt;
-      energy_total += p.n_tiles;
+      s.n_split = n_split;
+      score_total += (long long)p.n_tiles * Wt * n_split;
+      energy_total += (long long)p.n_tiles * n_split;
     }
   }
 
@@ -822,22 +858,27 @@ int b2i_align_launch(b2_ctx* h, const float* d_ref, const int64_t* ref_off, cons
       for (int k = 0; k < K; ++k) {
         const SelJob& s = sel[(size_t)b * K + k];
         if (s.kind != 0) continue;
-        SubJob jb;
-        jb.sub_off = s.sub_off;
-        jb.S = s.S;
-        jb.score_off = s.score_off + (long long)tile * Wt;
-        jb.spec_base = spec_base;
-        jb.blk_lo = (int)blk_lo;
-        jb.blk_hi = (int)std::min<long long>(blk_hi, ceil_div64(s.S, L));
-        jb.n_out = Wt;
-        jb.energy_slot = s.energy_slot + tile;
-        jb.bits_off = 0;
-        jb.hi = 0.f;
-        if (cue_mode) {
-          jb.bits_off = s.bits_off;
-          jb.hi = 2.f * s.sub_level - 1.f;  // the value load_block16 gives the float signal
+        const long long job_hi = std::min<long long>(blk_hi, ceil_div64(s.S, L));
+        const long long n_blk = std::max(0LL, job_hi - blk_lo);
+        for (int sp = 0; sp < n_split; ++sp) {
+          const long long c_lo = blk_lo + n_blk * sp / n_split, c_hi = blk_lo + n_blk * (sp + 1) / n_split;
+          SubJob jb;
+          jb.sub_off = s.sub_off;
+          jb.S = s.S;
+          jb.score_off = s.score_off + ((long long)sp * p.n_tiles + tile) * Wt;
+          jb.spec_base = spec_base + (c_lo - blk_lo);
+          jb.blk_lo = (int)c_lo;
+          jb.blk_hi = (int)c_hi;
+          jb.n_out = Wt;
+          jb.energy_slot = s.energy_slot + tile * n_split + sp;
+          jb.bits_off = 0;
+          jb.hi = 0.f;
+          if (cue_mode) {
+            jb.bits_off = s.bits_off;
+            jb.hi = 2.f * s.sub_level - 1.f;  // the value load_block16 gives the float signal
+          }
+          jobs.push_back(jb);
         }
-        jobs.push_back(jb);
       }
     }
   }
@@ -849,7 +890,7 @@ int b2i_align_launch(b2_ctx* h, const float* d_ref, const int64_t* ref_off, cons
   B2_TRY(b2i_meta_commit(&a));
   if (J >= (1u << 26)) B2_FAIL(h, B2_ERR_UNSUPPORTED, "align: B*K too large for one call");
   B2_CUDA(h, cudaMemsetAsync(work_count, 0, sizeof(int), h->stream));
-  window_max_kernel<<<(unsigned)J, 256, 0, h->stream>>>(d_sel, scores, job_energy, job_stat);
+  window_max_kernel<<<(unsigned)J, 256, 0, h->stream>>>(d_sel, scores, job_energy, job_stat, Wt);
   B2_CHECK_LAUNCH(h, "window_max_kernel");
   select_candidates_kernel<<<(unsigned)J, 256, 0, h->stream>>>(d_sel, scores, job_stat, K, winner_only,
                                                                 cand_off, cand_cnt, work_list, work_count);

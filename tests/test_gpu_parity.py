@@ -593,7 +593,8 @@ def test_sync_batch_small_vs_oracle(handle):
         assert np.array_equal(r[0], bs) and np.array_equal(r[1], bo) and np.array_equal(r[2], bk)
         assert np.array_equal(r[3], a_s) and np.array_equal(r[4], a_o)
     # rasterise-to-HBM fallback (float subtitle signals) vs the default in-kernel rasterisation
-    for env in ({"B2_FUSED_RASTER": "0"}, {"B2_FUSED_RASTER": "0", "B2_SUBBATCHES": "2"}):
+    for env in ({"B2_FUSED_RASTER": "0"}, {"B2_FUSED_RASTER": "0", "B2_SUBBATCHES": "2"},
+                {"B2_ALIGN_SPLIT": "1"}, {"B2_ALIGN_SPLIT": "5"}, {"B2_ALIGN_SPLIT": "2", "B2_FUSED_RASTER": "0"}):
         os.environ.update(env)
         try:
             r = handle.sync_batch(pcm, pcm_off, 16000, 100, 0.0, 100000, -1, -1, np.concatenate(cs),
@@ -722,3 +723,15 @@ def test_sync_two_hour_pair_recovers_offset(handle):
     for k in range(1, len(grid)):      # every ratio candidate: offset exact, score exact for +-1 x {-1, a}
         ws, wo = ao.fft_align(ref_sig, subs[k], 6000)
         assert a_o[k] == wo and _score_ok(a_s[k], ws)
+    # a single pair is split over CTAs by block ranges (8 chunks here by default); any other
+    # split, and none, must give bit-identical results (exact re-score, deterministic merge)
+    import os
+    for split in ("1", "3", "35", "40"):
+        os.environ["B2_ALIGN_SPLIT"] = split
+        try:
+            r = handle.sync_batch(pcm, [0, len(pcm)], 16000, 100, 0.0, 100000, -1, -1, st, en, None,
+                                  [0, len(st)], grid, 0.0, 6000, want_all=True)
+        finally:
+            del os.environ["B2_ALIGN_SPLIT"]
+        assert np.array_equal(r[0], bs) and np.array_equal(r[1], bo) and np.array_equal(r[2], bk)
+        assert np.array_equal(r[3], a_s) and np.array_equal(r[4], a_o), split
