@@ -350,7 +350,9 @@ __device__ __forceinline__ void sub_correlate_body(
 
 // Product kernel: accumulators in tensor memory, 96 registers per thread so that 16 K registers
 // and 88 KB of shared memory per SM stay free for a co-resident VAD CTA of the next sub-batch
-// (memory-bound VAD and FP32-bound correlation overlap on the same SMs).
+// (b2_sync_batch's optional sub-batch pipeline, B2_SUBBATCHES).  Measured: the co-resident VAD CTA
+// cannot keep enough bytes in flight in that space, the overlap gains 2 % (profiles/README.md), so
+// the pipeline is off by default; a 128-register variant of this kernel is not faster either.
 constexpr int kSubRegs = 96;
 __global__ void __maxnreg__(kSubRegs)
     sub_correlate_kernel(const float* __restrict__ sub, const SubJob* __restrict__ jobs,
