@@ -102,11 +102,9 @@ __global__ void __maxnreg__(96)  // leaves registers for a co-resident VAD CTA (
       const int lo = nx.i0 < 0 ? -nx.i0 : 0, hi = min(nx.R - nx.i0, kP);
       l2_prefetch_floats(ref + nx.ref_off + nx.i0 + lo, hi - lo);
     }
-    BlockSource s;
-    s.src = ref + it.ref_off + it.i0;
-    s.t_lo = it.i0 < 0 ? -it.i0 : 0;
-    s.t_hi = min(it.R - it.i0, kP);
-    float ss = forward_block(buf, t, tid, s);
+    float ss = float_pass1(buf, t, tid, ref + it.ref_off + it.i0, it.i0 < 0 ? -it.i0 : 0,
+                           min(it.R - it.i0, kP));
+    forward_rest(buf, t, tid);
     spec_store(buf, t, pc, tid, spec + (size_t)item * kPairs);
     for (int o = 16; o > 0; o >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o);
     if ((tid & 31) == 0) red[tid >> 5] = ss;
@@ -281,11 +279,8 @@ __device__ __forceinline__ void sub_correlate_body(
       const uint32_t* src = bits + (long long)(blk + 1) * wpb;
       if (more && tid < wpb) nw0 = __ldg(src + tid);
       if (more && tid + kThreads < wpb) nw1 = __ldg(src + tid + kThreads);
-      BitSource s;
-      s.words = bit_words + (blk & 1) * (kP / 32);
-      s.t_hi = min(job.S - j0, L);
-      s.hi = job.hi;
-      st.ss += forward_block(buf, t, tid, s);
+      st.ss += bits_pass1(buf, t, tid, bit_words + (blk & 1) * (kP / 32), min(job.S - j0, L), L, job.hi);
+      forward_rest(buf, t, tid);
     } else {
       BlockSource s;
       s.src = sub + job.sub_off + j0;
@@ -367,15 +362,6 @@ __global__ void __maxnreg__(kSubRegs)
                               const float* __restrict__ spec_energy, int L,
                               float* __restrict__ scores, float2* __restrict__ job_energy,
                               const uint32_t* __restrict__ sub_bits) {
-  sub_correlate_body<true, true>(nullptr, jobs, spec, spec_energy, L, scores, job_energy, sub_bits);
-}
-
-// A/B variant (B2_SUB_REGS=128): same body, the whole register file (TMEM accumulators kept).
-__global__ void __launch_bounds__(kThreads, 1)
-    sub_correlate_bits_r128_kernel(const SubJob* __restrict__ jobs, const float4* __restrict__ spec,
-                                   const float* __restrict__ spec_energy, int L,
-                                   float* __restrict__ scores, float2* __restrict__ job_energy,
-                                   const uint32_t* __restrict__ sub_bits) {
   sub_correlate_body<true, true>(nullptr, jobs, spec, spec_energy, L, scores, job_energy, sub_bits);
 }
 
@@ -725,11 +711,7 @@ int b2i_align_launch(b2_ctx* h, const float* d_ref, const int64_t* ref_off, cons
     B2_TRY(b2i_raster_bits_launch(h, cue_src, B, K, sub_off, bits_off.data(), d_bits));
     B2_CUDA(h, cudaFuncSetAttribute(sub_correlate_bits_kernel,
                                     cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytesBits));
-    B2_CUDA(h, cudaFuncSetAttribute(sub_correlate_bits_r128_kernel,
-                                    cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytesBits));
   }
-  const char* regs_env = getenv("B2_SUB_REGS");
-  const bool r128 = regs_env && atoi(regs_env) == 128;
 
   // score buffers + per-(pair,ratio) bookkeeping
   // Small batches: with fewer (pair, ratio, tile) jobs than SMs the block loop of a job (35 blocks
@@ -816,10 +798,7 @@ int b2i_align_launch(b2_ctx* h, const float* d_ref, const int64_t* ref_off, cons
                                                                     spec, spec_energy);
       B2_CHECK_LAUNCH(h, "ref_spectra_kernel");
     }
-    if (cue_mode && r128)
-      sub_correlate_bits_r128_kernel<<<(unsigned)jobs.size(), kThreads, kSmemBytesBits, h->stream>>>(
-          d_jobs, spec, spec_energy, L, scores, job_energy, d_bits);
-    else if (cue_mode)
+    if (cue_mode)
       sub_correlate_bits_kernel<<<(unsigned)jobs.size(), kThreads, kSmemBytesBits, h->stream>>>(
           d_jobs, spec, spec_energy, L, scores, job_energy, d_bits);
     else if (h->acc_in_tmem)

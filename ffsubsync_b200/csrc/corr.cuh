@@ -366,6 +366,52 @@ CORR_HD void load_block16(const BitSource& s, int j, float2 (&v)[16]) {
   }
 }
 
+// A FULL bit-mask block (t_hi == L, every block of a signal but its last): which samples are zero
+// padding is then a function of q alone, except for the one q that straddles L.  QB = L / 2048 is a
+// compile-time constant: q < QB needs no range test (2048 (q + 1) <= L), q > QB is all padding.
+// (r1k profile: the range tests were half of the 12 instructions spent per q on decoding.)
+template <int QB>
+struct BitSourceFull {
+  const uint32_t* words;
+  int L;
+  float hi;
+};
+template <int QB>
+CORR_HD void load_block16(const BitSourceFull<QB>& s, int j, float2 (&v)[16]) {
+  const int sh = 2 * (j & 15);
+  const uint32_t* w = s.words + (j >> 4);
+#pragma unroll
+  for (int q = 0; q < 16; ++q) {
+    if (q < QB) {
+      const uint32_t m = w[q << 6] >> sh;
+      v[q].x = (m & 1u) ? s.hi : -1.f;
+      v[q].y = (m & 2u) ? s.hi : -1.f;
+    } else if (q == QB) {
+      const int t0 = 2 * (j + (q << 10));
+      const uint32_t m = w[q << 6] >> sh;
+      v[q].x = t0 < s.L ? ((m & 1u) ? s.hi : -1.f) : 0.f;
+      v[q].y = t0 + 1 < s.L ? ((m & 2u) ? s.hi : -1.f) : 0.f;
+    } else {
+      v[q] = make_float2(0.f, 0.f);
+    }
+  }
+}
+
+// A float block that lies entirely inside its signal and starts 8-byte aligned (the interior
+// blocks of a reference signal): no clamping, no masking.
+struct BlockSourceFull {
+  const float2* src2;
+};
+CORR_HD void load_block16(const BlockSourceFull& s, int j, float2 (&v)[16]) {
+#pragma unroll
+  for (int q = 0; q < 16; ++q) v[q] = CORR_LDG(s.src2 + j + (q << 10));
+#pragma unroll
+  for (int q = 0; q < 16; ++q) {
+    v[q].x = 2.f * v[q].x - 1.f;
+    v[q].y = 2.f * v[q].y - 1.f;
+  }
+}
+
 // First DIF pass (span 16384) reading the block straight from its source (global memory for
 // float signals, the shared-memory copy of the block's speech bits in bit-mask mode).
 // Returns the thread's partial sum of squares of the (transformed) samples it loaded.
@@ -403,6 +449,49 @@ CORR_HD float forward_block(float2* buf, const Tables& t, int tid, const Source&
   r4_pass_smem<false>(buf, tid);
   CORR_SYNC();
   return ss;
+}
+
+// Passes 2..4 of the forward transform (everything after the first pass), trailing barrier included.
+CORR_HD void forward_rest(float2* buf, const Tables& t, int tid) {
+  CORR_SYNC();
+  dif16_pass_smem<6>(buf, t, tid);
+  CORR_SYNC();
+  dif16_pass_smem<2>(buf, t, tid);
+  CORR_SYNC();
+  r4_pass_smem<false>(buf, tid);
+  CORR_SYNC();
+}
+
+// First pass of a bit-mask block (uniform arguments): full blocks take the variant specialised for
+// L / 2048, the last block of a signal the general one.
+CORR_HD float bits_pass1(float2* buf, const Tables& t, int tid, const uint32_t* words, int t_hi, int L,
+                         float hi) {
+  if (t_hi == L) {
+    switch (L >> 11) {
+      case 8: return dif16_pass1_global(buf, t, tid, BitSourceFull<8>{words, L, hi});
+      case 9: return dif16_pass1_global(buf, t, tid, BitSourceFull<9>{words, L, hi});
+      case 10: return dif16_pass1_global(buf, t, tid, BitSourceFull<10>{words, L, hi});
+      case 11: return dif16_pass1_global(buf, t, tid, BitSourceFull<11>{words, L, hi});
+      case 12: return dif16_pass1_global(buf, t, tid, BitSourceFull<12>{words, L, hi});
+      case 13: return dif16_pass1_global(buf, t, tid, BitSourceFull<13>{words, L, hi});
+      case 14: return dif16_pass1_global(buf, t, tid, BitSourceFull<14>{words, L, hi});
+      case 15: return dif16_pass1_global(buf, t, tid, BitSourceFull<15>{words, L, hi});
+      case 16: return dif16_pass1_global(buf, t, tid, BitSourceFull<16>{words, L, hi});
+      default: break;
+    }
+  }
+  return dif16_pass1_global(buf, t, tid, BitSource{words, t_hi, hi});
+}
+
+// First pass of a float block whose sample t is src[t] for t in [t_lo, t_hi) (zero elsewhere).
+CORR_HD float float_pass1(float2* buf, const Tables& t, int tid, const float* src, int t_lo, int t_hi) {
+  if (t_lo == 0 && t_hi == kP && (reinterpret_cast<uintptr_t>(src) & 7) == 0)
+    return dif16_pass1_global(buf, t, tid, BlockSourceFull{reinterpret_cast<const float2*>(src)});
+  BlockSource s;
+  s.src = src;
+  s.t_lo = t_lo;
+  s.t_hi = t_hi;
+  return dif16_pass1_global(buf, t, tid, s);
 }
 
 // Packed half spectrum (x2) of the real block at an even position p and its partner q:

@@ -1,10 +1,12 @@
 // CPU emulation of the two correlation kernels of ffsubsync_b200/csrc/corr.cu: the very same
 // __host__ __device__ phase functions (corr.cuh) are run for tid = 0..511 with a loop standing
 // in for each __syncthreads-separated phase.  Test infrastructure (the build container has no
-// GPU); tests/test_corr_emul.py drives it.
+// GPU); tests/test_host_cpu.py drives it.
 //
 // usage: corr_emul in.bin out.bin
-// in.bin : int32 R, S, o_t, W, L ; float ref[R] ; float sub[S]
+// in.bin : int32 R, S, o_t, W, L, mode ; float ref[R] ; float sub[S]
+//          mode 0: float subtitle signal (sub_correlate_kernel);  mode 1: two-level subtitle signal
+//          {0, level} fed as a bit mask (sub_correlate_bits_kernel; L must be a multiple of 32)
 // out.bin: float c[W]  (c[m] ~ sum_j sub'[j] ref'[j + o_t + m]) ; float Es, Er
 #include <stdio.h>
 #include <stdlib.h>
@@ -14,8 +16,7 @@
 
 using namespace corr;
 
-static void forward_all(float2* buf, const Tables& t, const BlockSource& s, float* ss) {
-  for (int tid = 0; tid < kThreads; ++tid) ss[tid] += dif16_pass1_global(buf, t, tid, s);
+static void rest_all(float2* buf, const Tables& t) {
   for (int tid = 0; tid < kThreads; ++tid) dif16_pass_smem<6>(buf, t, tid);
   for (int tid = 0; tid < kThreads; ++tid) dif16_pass_smem<2>(buf, t, tid);
   for (int tid = 0; tid < kThreads; ++tid) r4_pass_smem<false>(buf, tid);
@@ -25,13 +26,14 @@ int main(int argc, char** argv) {
   if (argc != 3) return 2;
   FILE* f = fopen(argv[1], "rb");
   if (!f) return 3;
-  int hdr[5];
-  if (fread(hdr, 4, 5, f) != 5) return 4;
-  const int R = hdr[0], S = hdr[1], o_t = hdr[2], W = hdr[3], L = hdr[4];
+  int hdr[6];
+  if (fread(hdr, 4, 6, f) != 6) return 4;
+  const int R = hdr[0], S = hdr[1], o_t = hdr[2], W = hdr[3], L = hdr[4], mode = hdr[5];
   std::vector<float> ref(R), sub(S);
   if (fread(ref.data(), 4, R, f) != (size_t)R) return 4;
   if (fread(sub.data(), 4, S, f) != (size_t)S) return 4;
   fclose(f);
+  if (mode == 1 && (L & 31)) return 5;
 
   std::vector<float2> buf(kM), tw(1024), fine(32);
   for (int tid = 0; tid < kThreads; ++tid) init_tables(tw.data(), fine.data(), tid);
@@ -40,22 +42,39 @@ int main(int argc, char** argv) {
   for (auto& s : st) sub_state_clear(s);
   std::vector<float4> spec(kPairs);
   std::vector<float> ss_ref(kThreads, 0.f), ss_sub(kThreads, 0.f);
+  float level = 0.f;
+  for (float v : sub) level = v > level ? v : level;
+  std::vector<uint32_t> words(kP / 32);
 
   const int nblk = (S + L - 1) / L;
   for (int blk = 0; blk < nblk; ++blk) {
     const int j0 = blk * L, i0 = j0 + o_t;
     if (i0 >= R || i0 + kP <= 0) continue;  // block pruning, as the host planner does
-    BlockSource rs;
-    rs.src = ref.data() + i0;
-    rs.t_lo = i0 < 0 ? -i0 : 0;
-    rs.t_hi = (R - i0) < kP ? (R - i0) : kP;
-    forward_all(buf.data(), t, rs, ss_ref.data());
+    // reference block (ref_spectra_kernel)
+    const int r_lo = i0 < 0 ? -i0 : 0, r_hi = (R - i0) < kP ? (R - i0) : kP;
+    for (int tid = 0; tid < kThreads; ++tid)
+      ss_ref[tid] += float_pass1(buf.data(), t, tid, ref.data() + i0, r_lo, r_hi);
+    rest_all(buf.data(), t);
     for (int tid = 0; tid < kThreads; ++tid) spec_store(buf.data(), t, pair_ctx(tid), tid, spec.data());
-    BlockSource bs;
-    bs.src = sub.data() + j0;
-    bs.t_lo = 0;
-    bs.t_hi = (S - j0) < L ? (S - j0) : L;
-    forward_all(buf.data(), t, bs, ss_sub.data());
+    // subtitle block
+    const int t_hi = (S - j0) < L ? (S - j0) : L;
+    if (mode == 1) {
+      for (auto& w : words) w = 0xdeadbeefu;  // stale words beyond the block must not matter
+      for (int w = 0; w < L / 32; ++w) {
+        uint32_t bits = 0;
+        for (int b = 0; b < 32; ++b) {
+          const int tt = 32 * w + b;
+          if (tt < t_hi && sub[j0 + tt] != 0.f) bits |= 1u << b;
+        }
+        words[w] = bits;
+      }
+      for (int tid = 0; tid < kThreads; ++tid)
+        ss_sub[tid] += bits_pass1(buf.data(), t, tid, words.data(), t_hi, L, 2.f * level - 1.f);
+    } else {
+      for (int tid = 0; tid < kThreads; ++tid)
+        ss_sub[tid] += float_pass1(buf.data(), t, tid, sub.data() + j0, 0, t_hi);
+    }
+    rest_all(buf.data(), t);
     for (int tid = 0; tid < kThreads; ++tid) sub_accumulate(st[tid], buf.data(), t, pair_ctx(tid), tid, spec.data());
   }
   for (int tid = 0; tid < kThreads; ++tid) sub_retangle_store(st[tid], buf.data(), t, pair_ctx(tid), tid);

@@ -164,13 +164,14 @@ def test_scaler_roundtrip(golden):
 
 # --------------------------------------------------------- CPU emulation of the FFT kernel chain
 
-def _emulate(ref, sub, o_t, W):
+def _emulate(ref, sub, o_t, W, mode=0):
     P = 32768
-    L = P - (W | 1) + 1
+    # the planner's rule: offsets per tile = 1 (mod 32), so L is a multiple of 32 (bit-mask words)
+    L = P - (32 * ((W + 30) // 32) + 1) + 1 if mode == 1 else P - (W | 1) + 1
     tmp = os.path.join(ROOT, "tests", "host_emul")
     fin, fout = os.path.join(tmp, "_in.bin"), os.path.join(tmp, "_out.bin")
     with open(fin, "wb") as f:
-        f.write(struct.pack("5i", len(ref), len(sub), o_t, W, L))
+        f.write(struct.pack("6i", len(ref), len(sub), o_t, W, L, mode))
         f.write(np.asarray(ref, np.float32).tobytes())
         f.write(np.asarray(sub, np.float32).tobytes())
     subprocess.check_call([os.path.join(tmp, "corr_emul"), fin, fout])
@@ -187,18 +188,24 @@ def _direct(ref, sub, o_t, W):
     return np.array([full[o % n] if -len(s) < o < len(r) else 0.0 for o in range(o_t, o_t + W)])
 
 
+@pytest.mark.parametrize("mode", [0, 1])
 @pytest.mark.parametrize("R,S,o_t,W", [(11, 6, -6, 16), (300, 250, -20, 41), (60000, 61000, -5999, 12000),
-                                       (50000, 70000, -16000, 16385), (40000, 40000, 20000, 16385)])
-def test_kernel_chain_emulation(built, R, S, o_t, W):
+                                       (50000, 70000, -16000, 16385), (40000, 40000, 20000, 16385),
+                                       (90000, 80000, -3000, 7000), (5000, 4000, 17, 1),
+                                       (70000, 66000, -2000, 4000)])
+def test_kernel_chain_emulation(built, R, S, o_t, W, mode):
     """The exact __host__ __device__ kernel code, run thread by thread on the CPU, reproduces the
-    float64 correlation within the round-off bound the candidate selection assumes."""
+    float64 correlation within the round-off bound the candidate selection assumes.  mode 0: float
+    subtitle signal; mode 1: the same two-level signal as a bit mask (full blocks take the first-pass
+    variants specialised for L / 2048 = 8, 10, 12, 14, 15, 16 here; interior aligned reference blocks
+    the unmasked loader)."""
     rng = np.random.RandomState(R + S)
     ref = (rng.rand(R) > 0.5).astype(np.float32)
     sub = (rng.rand(S) > 0.5).astype(np.float32) * np.float32(0.96)
     if R > 1000:
         k = min(R, S) - 1234
         sub[1234:1234 + k] = ref[:k] * np.float32(0.96)
-    got, es, er = _emulate(ref, sub, o_t, W)
+    got, es, er = _emulate(ref, sub, o_t, W, mode)
     want = _direct(ref, sub, o_t, W)
     err = np.abs(got - want).max()
     bound = 2.0 ** -24 * np.sqrt(es * er)
