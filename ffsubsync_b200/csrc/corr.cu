@@ -174,12 +174,14 @@ __device__ __forceinline__ void tmem_wait_st() {
 // acc (tensor memory) += conj(A) * B for one block.  Column group g holds the thread's pair slots
 // 4g..4g+3 as (cp.x, cp.y, cq.x, cq.y) each; the load of group g+1 is in flight while group g is
 // updated.  FIRST: nothing accumulated yet, start from zero instead of loading.
-template <bool FIRST>
+// DEPTH = how many slots ahead the stored reference spectrum is read (L2 latency under full load).
+template <bool FIRST, int DEPTH>
 __device__ __forceinline__ void accumulate_block_tmem(uint32_t taddr, const float2* buf,
                                                       const Tables& t, const PairCtx& pc, int tid,
                                                       const float4* __restrict__ spec) {
-  float4 b0 = __ldg(spec + tid);
-  float4 b1 = __ldg(spec + tid + kThreads);
+  float4 bq[DEPTH];
+#pragma unroll
+  for (int d = 0; d < DEPTH; ++d) bq[d] = __ldg(spec + tid + d * kThreads);
   float cur[16], nxt[16];
   if (!FIRST) {
     tmem_ld16(taddr, cur);
@@ -196,9 +198,8 @@ __device__ __forceinline__ void accumulate_block_tmem(uint32_t taddr, const floa
 #pragma unroll
     for (int uu = 0; uu < 4; ++uu) {
       const int u = 4 * g + uu;
-      const float4 b = b0;
-      b0 = b1;
-      if (u + 2 < 16) b1 = __ldg(spec + tid + (u + 2) * kThreads);
+      const float4 b = bq[u % DEPTH];
+      if (u + DEPTH < 16) bq[u % DEPTH] = __ldg(spec + tid + (u + DEPTH) * kThreads);
       float2 dp, dq;
       product_terms(buf, t, pc, tid, u, b, dp, dq);
       cur[4 * uu + 0] += dp.x;
@@ -221,7 +222,7 @@ __device__ __forceinline__ void accumulate_block_tmem(uint32_t taddr, const floa
 //   K masks of a pair straight from the cue list, 1/32 of the bytes of the float signals, and the
 //   exact re-score reads the same masks).  The words of block blk+1 are fetched while block blk is
 //   transformed (registers -> shared memory, double buffered).
-template <bool TMEM, bool BITS>
+template <bool TMEM, bool BITS, int DEPTH = 2>
 __device__ __forceinline__ void sub_correlate_body(
     const float* __restrict__ sub, const SubJob* __restrict__ jobs, const float4* __restrict__ spec,
     const float* __restrict__ spec_energy, int L, float* __restrict__ scores,
@@ -290,8 +291,8 @@ __device__ __forceinline__ void sub_correlate_body(
     }
     const size_t item = (size_t)(job.spec_base + (blk - job.blk_lo));
     if (TMEM) {
-      if (blk == job.blk_lo) accumulate_block_tmem<true>(taddr, buf, t, pc, tid, spec + item * kPairs);
-      else accumulate_block_tmem<false>(taddr, buf, t, pc, tid, spec + item * kPairs);
+      if (blk == job.blk_lo) accumulate_block_tmem<true, DEPTH>(taddr, buf, t, pc, tid, spec + item * kPairs);
+      else accumulate_block_tmem<false, DEPTH>(taddr, buf, t, pc, tid, spec + item * kPairs);
     } else {
       sub_accumulate(st, buf, t, pc, tid, spec + item * kPairs);
     }
@@ -363,6 +364,22 @@ __global__ void __maxnreg__(kSubRegs)
                               float* __restrict__ scores, float2* __restrict__ job_energy,
                               const uint32_t* __restrict__ sub_bits) {
   sub_correlate_body<true, true>(nullptr, jobs, spec, spec_energy, L, scores, job_energy, sub_bits);
+}
+
+// A/B variants (B2_SPEC_DEPTH=4 / 8): reference spectrum read 4 / 8 slots ahead, no register cap.
+__global__ void __launch_bounds__(kThreads, 1)
+    sub_correlate_bits_d4_kernel(const SubJob* __restrict__ jobs, const float4* __restrict__ spec,
+                                 const float* __restrict__ spec_energy, int L,
+                                 float* __restrict__ scores, float2* __restrict__ job_energy,
+                                 const uint32_t* __restrict__ sub_bits) {
+  sub_correlate_body<true, true, 4>(nullptr, jobs, spec, spec_energy, L, scores, job_energy, sub_bits);
+}
+__global__ void __launch_bounds__(kThreads, 1)
+    sub_correlate_bits_d8_kernel(const SubJob* __restrict__ jobs, const float4* __restrict__ spec,
+                                 const float* __restrict__ spec_energy, int L,
+                                 float* __restrict__ scores, float2* __restrict__ job_energy,
+                                 const uint32_t* __restrict__ sub_bits) {
+  sub_correlate_body<true, true, 8>(nullptr, jobs, spec, spec_energy, L, scores, job_energy, sub_bits);
 }
 
 // A/B variant (B2_ACC=reg): accumulators in registers, 128 registers per thread.
@@ -711,7 +728,13 @@ int b2i_align_launch(b2_ctx* h, const float* d_ref, const int64_t* ref_off, cons
     B2_TRY(b2i_raster_bits_launch(h, cue_src, B, K, sub_off, bits_off.data(), d_bits));
     B2_CUDA(h, cudaFuncSetAttribute(sub_correlate_bits_kernel,
                                     cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytesBits));
+    B2_CUDA(h, cudaFuncSetAttribute(sub_correlate_bits_d4_kernel,
+                                    cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytesBits));
+    B2_CUDA(h, cudaFuncSetAttribute(sub_correlate_bits_d8_kernel,
+                                    cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytesBits));
   }
+  const char* depth_env = getenv("B2_SPEC_DEPTH");
+  const int spec_depth = depth_env ? atoi(depth_env) : 2;
 
   // score buffers + per-(pair,ratio) bookkeeping
   // Small batches: with fewer (pair, ratio, tile) jobs than SMs the block loop of a job (35 blocks
@@ -798,7 +821,13 @@ int b2i_align_launch(b2_ctx* h, const float* d_ref, const int64_t* ref_off, cons
                                                                     spec, spec_energy);
       B2_CHECK_LAUNCH(h, "ref_spectra_kernel");
     }
-    if (cue_mode)
+    if (cue_mode && spec_depth == 4)
+      sub_correlate_bits_d4_kernel<<<(unsigned)jobs.size(), kThreads, kSmemBytesBits, h->stream>>>(
+          d_jobs, spec, spec_energy, L, scores, job_energy, d_bits);
+    else if (cue_mode && spec_depth == 8)
+      sub_correlate_bits_d8_kernel<<<(unsigned)jobs.size(), kThreads, kSmemBytesBits, h->stream>>>(
+          d_jobs, spec, spec_energy, L, scores, job_energy, d_bits);
+    else if (cue_mode)
       sub_correlate_bits_kernel<<<(unsigned)jobs.size(), kThreads, kSmemBytesBits, h->stream>>>(
           d_jobs, spec, spec_energy, L, scores, job_energy, d_bits);
     else if (h->acc_in_tmem)
