@@ -174,7 +174,8 @@ __device__ __forceinline__ void tmem_wait_st() {
 // acc (tensor memory) += conj(A) * B for one block.  Column group g holds the thread's pair slots
 // 4g..4g+3 as (cp.x, cp.y, cq.x, cq.y) each; the load of group g+1 is in flight while group g is
 // updated.  FIRST: nothing accumulated yet, start from zero instead of loading.
-// DEPTH = how many slots ahead the stored reference spectrum is read (L2 latency under full load).
+// DEPTH = how many slots ahead the stored reference spectrum is read (measured on the 148-pair
+// bench: 2, 4 and 8 give 7.20 / 7.23 / 7.23 ms per step - the loads are not the limiter).
 template <bool FIRST, int DEPTH>
 __device__ __forceinline__ void accumulate_block_tmem(uint32_t taddr, const float2* buf,
                                                       const Tables& t, const PairCtx& pc, int tid,
@@ -364,22 +365,6 @@ __global__ void __maxnreg__(kSubRegs)
                               float* __restrict__ scores, float2* __restrict__ job_energy,
                               const uint32_t* __restrict__ sub_bits) {
   sub_correlate_body<true, true>(nullptr, jobs, spec, spec_energy, L, scores, job_energy, sub_bits);
-}
-
-// A/B variants (B2_SPEC_DEPTH=4 / 8): reference spectrum read 4 / 8 slots ahead, no register cap.
-__global__ void __launch_bounds__(kThreads, 1)
-    sub_correlate_bits_d4_kernel(const SubJob* __restrict__ jobs, const float4* __restrict__ spec,
-                                 const float* __restrict__ spec_energy, int L,
-                                 float* __restrict__ scores, float2* __restrict__ job_energy,
-                                 const uint32_t* __restrict__ sub_bits) {
-  sub_correlate_body<true, true, 4>(nullptr, jobs, spec, spec_energy, L, scores, job_energy, sub_bits);
-}
-__global__ void __launch_bounds__(kThreads, 1)
-    sub_correlate_bits_d8_kernel(const SubJob* __restrict__ jobs, const float4* __restrict__ spec,
-                                 const float* __restrict__ spec_energy, int L,
-                                 float* __restrict__ scores, float2* __restrict__ job_energy,
-                                 const uint32_t* __restrict__ sub_bits) {
-  sub_correlate_body<true, true, 8>(nullptr, jobs, spec, spec_energy, L, scores, job_energy, sub_bits);
 }
 
 // A/B variant (B2_ACC=reg): accumulators in registers, 128 registers per thread.
@@ -728,13 +713,7 @@ int b2i_align_launch(b2_ctx* h, const float* d_ref, const int64_t* ref_off, cons
     B2_TRY(b2i_raster_bits_launch(h, cue_src, B, K, sub_off, bits_off.data(), d_bits));
     B2_CUDA(h, cudaFuncSetAttribute(sub_correlate_bits_kernel,
                                     cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytesBits));
-    B2_CUDA(h, cudaFuncSetAttribute(sub_correlate_bits_d4_kernel,
-                                    cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytesBits));
-    B2_CUDA(h, cudaFuncSetAttribute(sub_correlate_bits_d8_kernel,
-                                    cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytesBits));
   }
-  const char* depth_env = getenv("B2_SPEC_DEPTH");
-  const int spec_depth = depth_env ? atoi(depth_env) : 2;
 
   // score buffers + per-(pair,ratio) bookkeeping
   // Small batches: with fewer (pair, ratio, tile) jobs than SMs the block loop of a job (35 blocks
@@ -821,13 +800,7 @@ int b2i_align_launch(b2_ctx* h, const float* d_ref, const int64_t* ref_off, cons
                                                                     spec, spec_energy);
       B2_CHECK_LAUNCH(h, "ref_spectra_kernel");
     }
-    if (cue_mode && spec_depth == 4)
-      sub_correlate_bits_d4_kernel<<<(unsigned)jobs.size(), kThreads, kSmemBytesBits, h->stream>>>(
-          d_jobs, spec, spec_energy, L, scores, job_energy, d_bits);
-    else if (cue_mode && spec_depth == 8)
-      sub_correlate_bits_d8_kernel<<<(unsigned)jobs.size(), kThreads, kSmemBytesBits, h->stream>>>(
-          d_jobs, spec, spec_energy, L, scores, job_energy, d_bits);
-    else if (cue_mode)
+    if (cue_mode)
       sub_correlate_bits_kernel<<<(unsigned)jobs.size(), kThreads, kSmemBytesBits, h->stream>>>(
           d_jobs, spec, spec_energy, L, scores, job_energy, d_bits);
     else if (h->acc_in_tmem)
