@@ -108,7 +108,8 @@ class ClockSampler:
             self.nvml_thread.join(1.0)
             clocks = [c for c, _ in self.nvml_samples]
             reasons = sorted({r for _, rs in self.nvml_samples for r in rs})
-            return {"sm_mhz": float(np.median(clocks)) if clocks else None, "sm_max_mhz": float(self.sm_max),
+            return {"sm_mhz": float(np.median(clocks)) if clocks else None,
+                    "sm_min_mhz": float(min(clocks)) if clocks else None, "sm_max_mhz": float(self.sm_max),
                     "samples": len(clocks), "reasons": reasons, "source": "nvml, sampled during the timed region"}
         if self.proc is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
