@@ -11,7 +11,8 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 from ffsubsync_b200 import _native  # noqa: E402
 
-FPW, FR = 160, 16000
+FR = int(os.environ.get("VAD_TUNE_FR", "16000"))   # e.g. 48000: ffsubsync's default frame rate
+FPW = FR // 100
 
 
 def main():
