@@ -316,11 +316,19 @@ class VideoSpeechTransformer(TransformerMixin):
                     pushed += 1
                 else:
                     media_bstring.append(detector(np.frombuffer(in_bytes, np.uint8)))
+        except BaseException:
+            if streaming and pushed:  # close the device-side stream without masking the error
+                try:
+                    detector.stream_end()
+                except Exception:
+                    pass
+                pushed = 0
+            raise
         finally:
             if closer is not None:
                 closer()
-            if streaming and pushed:
-                media_bstring.append(detector.stream_end())
+        if streaming and pushed:
+            media_bstring.append(detector.stream_end())
         if len(media_bstring) == 0:
             raise ValueError(
                 "Unable to detect speech. "
