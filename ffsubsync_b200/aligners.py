@@ -88,32 +88,34 @@ class MaxScoreAligner(TransformerMixin):
         sample_rate=None,
         max_offset_seconds=None,
     ) -> None:
-        self.srtin: Optional[str] = srtin
-        if sample_rate is None or max_offset_seconds is None:
-            self.max_offset_samples: Optional[int] = None
-        else:
-            self.max_offset_samples = abs(int(max_offset_seconds * sample_rate))
-        if isinstance(base_aligner, type):
-            self.base_aligner: FFTAligner = base_aligner(max_offset_samples=self.max_offset_samples)
-        else:
-            self.base_aligner = base_aligner
+        # aligners.py:90-109: seconds -> samples (None when either is missing); an aligner CLASS is
+        # instantiated with that mask, an INSTANCE is used as it is
+        have_mask = sample_rate is not None and max_offset_seconds is not None
+        self.max_offset_samples: Optional[int] = (
+            abs(int(max_offset_seconds * sample_rate)) if have_mask else None)
         self.max_offset_seconds: Optional[int] = max_offset_seconds
+        self.srtin: Optional[str] = srtin
+        self.base_aligner: FFTAligner = (
+            base_aligner(max_offset_samples=self.max_offset_samples)
+            if isinstance(base_aligner, type) else base_aligner)
         self._scores: List[Tuple[Tuple[float, int], Pipeline]] = []
 
     def _align_one(self, refstring, substring) -> Tuple[float, int]:
         return self.base_aligner.fit_transform(refstring, substring, get_score=True)
 
     def fit_gss(self, refstring, subpipe_maker):
-        def opt_func(framerate_ratio, is_last_iter):
-            subpipe = subpipe_maker(framerate_ratio)
-            substring = subpipe.fit_transform(self.srtin)
-            score = self._align_one(refstring, substring)
-            logger.info("got score %.0f (offset %d) for ratio %.3f", score[0], score[1], framerate_ratio)
-            if is_last_iter:
-                self._scores.append((score, subpipe))
-            return -score[0]
+        """Golden-section search over the framerate ratio (aligners.py:111-129): 17 evaluations of
+        rescale -> rasterise -> align on [0.9, 1.1]; only the last one is kept in ``_scores``."""
 
-        gss(opt_func, MIN_FRAMERATE_RATIO, MAX_FRAMERATE_RATIO)
+        def negative_score(ratio: float, final: bool) -> float:
+            pipe = subpipe_maker(ratio)
+            result = self._align_one(refstring, pipe.fit_transform(self.srtin))
+            logger.info("got score %.0f (offset %d) for ratio %.3f", result[0], result[1], ratio)
+            if final:
+                self._scores.append((result, pipe))
+            return -result[0]
+
+        gss(negative_score, MIN_FRAMERATE_RATIO, MAX_FRAMERATE_RATIO)
         return self
 
     def fit(self, refstring, subpipes: Union[Pipeline, List[Pipeline]]) -> "MaxScoreAligner":
@@ -153,13 +155,13 @@ class MaxScoreAligner(TransformerMixin):
         return self
 
     def transform(self, *_) -> Tuple[Tuple[float, float], Pipeline]:
-        scores = self._scores
-        if self.max_offset_samples is not None:
-            scores = [s for s in scores if abs(s[0][1]) <= self.max_offset_samples]
-        if len(scores) == 0:
+        # aligners.py:154-167: drop candidates beyond the offset limit, highest score wins, the
+        # first in list order on equal scores (max() keeps the first maximum)
+        limit = self.max_offset_samples
+        kept = [c for c in self._scores if limit is None or abs(c[0][1]) <= limit]
+        if not kept:
             raise FailedToFindAlignmentException(
-                "Synchronization failed; consider passing "
-                "--max-offset-seconds with a number larger than "
-                "{}".format(self.max_offset_seconds))
-        (score, offset), subpipe = max(scores, key=lambda x: x[0][0])
-        return (score, offset), subpipe
+                "Synchronization failed; consider passing --max-offset-seconds with a number larger "
+                "than {}".format(self.max_offset_seconds))
+        best = max(kept, key=lambda c: c[0][0])
+        return (best[0][0], best[0][1]), best[1]
