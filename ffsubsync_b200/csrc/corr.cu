@@ -94,7 +94,7 @@ __global__ void __maxnreg__(96)  // leaves registers for a co-resident VAD CTA (
   init_tables(tw1024, fine32, tid);
   __syncthreads();
   const Tables t{tw1024, fine32};
-  const PairCtx pc = pair_ctx(tid);
+  const PairCtx pc = pair_ctx(t, tid);
   for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
     const SpecItem it = items[item];
     if (tid == 0 && item + (int)gridDim.x < n_items) {
@@ -263,7 +263,7 @@ __device__ __forceinline__ void sub_correlate_body(
     taddr = tmem_base_s + (uint32_t)(((warp & 3) * 32) << 16) + (uint32_t)((warp >> 2) * 64);
   }
   const Tables t{tw1024, fine32};
-  const PairCtx pc = pair_ctx(tid);
+  const PairCtx pc = pair_ctx(t, tid);
   SubState st;
   sub_state_clear(st);
   float er = 0.f;

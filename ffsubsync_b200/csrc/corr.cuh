@@ -545,13 +545,19 @@ struct PairCtx {
   int sq0;     // swz(1023 - 2 tid)
   int sq_u0;   // swz(partner of position 2 tid)     (u = 0, tid >= 2)
   int f_base;  // freq_of_pos(2 tid): low 4 bits are zero
+  // w^f_base.  The twiddle of slot u is w^(f_base | u) = w_base * fine32[u]: one broadcast table
+  // read per slot.  (Reading tw1024[(f_base | u) >> 5] per slot was an 8-way bank conflict - the
+  // digit-reversed f_base of neighbouring threads differ by multiples of 256 - and 43 % of the
+  // product phase's shared-memory wavefronts, r1m full-load capture.)
+  float2 w_base;
 };
-CORR_HD PairCtx pair_ctx(int tid) {
+CORR_HD PairCtx pair_ctx(const Tables& t, int tid) {  // after init_tables + barrier
   PairCtx c;
   c.sp0 = swz(2 * tid);
   c.sq0 = swz(1023 - 2 * tid);
   c.sq_u0 = swz(partner_pos(2 * tid));
   c.f_base = freq_of_pos(2 * tid);
+  c.w_base = twiddle15(t, c.f_base);
   return c;
 }
 
@@ -572,7 +578,7 @@ CORR_HD void untangle_slot(const float2* buf, const Tables& t, const PairCtx& c,
   const float2 zq = buf[u == 0 ? c.sq_u0 : c.sq0 + ((16 - u) << 10)];
   const float2 e = make_float2(zp.x + zq.x, zp.y - zq.y);
   const float2 d = make_float2(zp.x - zq.x, zp.y + zq.y);
-  const float2 tt = cmul(twiddle15(t, c.f_base | u), d);
+  const float2 tt = cmul(cmul(c.w_base, t.fine32[u]), d);
   hp = make_float2(e.x + tt.y, e.y - tt.x);
   hq = make_float2(e.x - tt.y, -e.y - tt.x);
 }
@@ -673,7 +679,7 @@ CORR_HD void sub_retangle_store(const SubState& st, float2* buf, const Tables& t
       const float2 cp = st.cp[u], cq = st.cq[u];
       const float2 e = make_float2(cp.x + cq.x, cp.y - cq.y);
       const float2 d = make_float2(cp.x - cq.x, cp.y + cq.y);
-      const float2 tt = cmul(cconj(twiddle15(t, c.f_base | u)), d);
+      const float2 tt = cmul(cconj(cmul(c.w_base, t.fine32[u])), d);
       buf[c.sp0 + (u << 10)] = make_float2(e.x - tt.y, e.y + tt.x);
       buf[u == 0 ? c.sq_u0 : c.sq0 + ((16 - u) << 10)] = make_float2(e.x + tt.y, -e.y + tt.x);
     }

@@ -55,7 +55,7 @@ int main(int argc, char** argv) {
     for (int tid = 0; tid < kThreads; ++tid)
       ss_ref[tid] += float_pass1(buf.data(), t, tid, ref.data() + i0, r_lo, r_hi);
     rest_all(buf.data(), t);
-    for (int tid = 0; tid < kThreads; ++tid) spec_store(buf.data(), t, pair_ctx(tid), tid, spec.data());
+    for (int tid = 0; tid < kThreads; ++tid) spec_store(buf.data(), t, pair_ctx(t, tid), tid, spec.data());
     // subtitle block
     const int t_hi = (S - j0) < L ? (S - j0) : L;
     if (mode == 1) {
@@ -75,9 +75,9 @@ int main(int argc, char** argv) {
         ss_sub[tid] += float_pass1(buf.data(), t, tid, sub.data() + j0, 0, t_hi);
     }
     rest_all(buf.data(), t);
-    for (int tid = 0; tid < kThreads; ++tid) sub_accumulate(st[tid], buf.data(), t, pair_ctx(tid), tid, spec.data());
+    for (int tid = 0; tid < kThreads; ++tid) sub_accumulate(st[tid], buf.data(), t, pair_ctx(t, tid), tid, spec.data());
   }
-  for (int tid = 0; tid < kThreads; ++tid) sub_retangle_store(st[tid], buf.data(), t, pair_ctx(tid), tid);
+  for (int tid = 0; tid < kThreads; ++tid) sub_retangle_store(st[tid], buf.data(), t, pair_ctx(t, tid), tid);
   for (int tid = 0; tid < kThreads; ++tid) inverse_passes_1(buf.data(), tid);
   for (int tid = 0; tid < kThreads; ++tid) inverse_passes_2(buf.data(), t, tid);
   for (int tid = 0; tid < kThreads; ++tid) inverse_passes_3(buf.data(), t, tid);
