@@ -201,7 +201,13 @@ template <int SUB_LOG2>
 CORR_HD float2 pass_twiddle(const Tables& t, int j) {
   if (SUB_LOG2 == 10) return twiddle15(t, j << 1);  // span 16384
   if (SUB_LOG2 == 6) return t.tw1024[j];            // span 1024
-  return t.tw1024[j << 4];                          // span 64
+  // span 64: exp(-2 pi i j / 64), j = 0..3.  Four constants selected in registers: reading
+  // tw1024[16 j] is a 4-way bank conflict (4 addresses 128 bytes apart per warp).
+  const float c = j == 0 ? 1.f : j == 1 ? 0.99518472667219693f : j == 2 ? 0.98078528040323043f
+                                                                          : 0.95694033573220882f;
+  const float s = j == 0 ? 0.f : j == 1 ? -0.09801714032956060f : j == 2 ? -0.19509032201612825f
+                                                                           : -0.29028467725446233f;
+  return make_float2(c, s);
 }
 
 // Swizzled shared-memory index of element q of radix-16 butterfly u, without re-deriving the
