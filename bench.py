@@ -135,6 +135,97 @@ class ClockSampler:
 
 # ------------------------------------------------------------------------------------ GPU arm
 
+def default_pairs(world):
+    """BASELINE configs[2]: 256 two-hour pairs on one GPU; configs[3]: 4096 pairs over 8 GPUs =
+    512 per GPU.  (2 and 4 GPUs keep 256 per GPU.)  B2_BENCH_PAIRS / --pairs override."""
+    env = os.environ.get("B2_BENCH_PAIRS")
+    if env:
+        return int(env)
+    return 512 if world >= 8 else 256
+
+
+_CHECK_JOBS = []   # filled before the worker pool forks (the PCM of a pair is 230 MB: inherited, not pickled)
+
+
+def _oracle_check_worker(index):
+    """Checker (untimed): one sampled pair through the oracle - numpy detector in 100 s chunks, the
+    reference's scaler + rasteriser per ratio, complex128 FFT aligner per ratio, max over ratios."""
+    from oracle import aligner_oracle as ao
+    from oracle import raster_oracle as ro
+    from oracle import vad_oracle as vo
+    pcm, starts, ends, ratios = _CHECK_JOBS[index]
+    chunk = 2 * FRAME_RATE // SAMPLE_RATE * 10000 // 2
+    ref = np.concatenate([vo.energy_zcr_detect(pcm[i:i + chunk], SAMPLE_RATE, FRAME_RATE, 0.0)
+                          for i in range(0, len(pcm), chunk)])
+    subs = [ro.rasterize(starts, ends, None, SAMPLE_RATE, 0, r)[0] for r in ratios]
+    mos = ao.max_offset_samples_of(SAMPLE_RATE, MAX_OFFSET_SECONDS)
+    per_ratio = [ao.fft_align(ref, sub, mos) for sub in subs]
+    k = ao.max_score_select(per_ratio, mos)
+    return per_ratio, k
+
+
+def verify_against_oracle(bs, pairs, pcm_d, pcm_off, ratios, n_sample, seed):
+    """Untimed parity check at the benchmarked batch size: the whole batch runs once with the
+    per-ratio outputs requested (every ratio re-scored exactly) and once winner-only (the timed
+    configuration); a seeded sample of pairs is compared with the oracle ratio by ratio (offset
+    exact, score within 1e-5 relative) and the winner triples of both runs must agree."""
+    import multiprocessing as mp
+    import torch
+    B, K = len(pcm_off) - 1, len(ratios)
+    dev = pcm_d.device
+    all_out = {"score": torch.empty(B * K, dtype=torch.float64, device=dev),
+               "offset": torch.empty(B * K, dtype=torch.int32, device=dev)}
+    full = bs.sync_device(pcm_d, pcm_off, pairs.cue_start, pairs.cue_end, pairs.cue_off, all_out=all_out)
+    torch.cuda.synchronize()
+    full = {k: v.cpu().numpy().copy() for k, v in full.items()}
+    a_score = all_out["score"].cpu().numpy().reshape(B, K)
+    a_off = all_out["offset"].cpu().numpy().reshape(B, K)
+    win = bs.sync_device(pcm_d, pcm_off, pairs.cue_start, pairs.cue_end, pairs.cue_off)
+    torch.cuda.synchronize()
+    win = {k: v.cpu().numpy() for k, v in win.items()}
+    same_winner = bool((win["best_offset"] == full["best_offset"]).all()
+                       and (win["best_k"] == full["best_k"]).all()
+                       and (win["best_score"] == full["best_score"]).all())
+    rng = np.random.RandomState(seed)
+    sample = sorted(rng.choice(B, size=min(n_sample, B), replace=False).tolist())
+    jobs = []
+    for b in sample:
+        pcm = pcm_d[int(pcm_off[b]):int(pcm_off[b + 1])].cpu().numpy()
+        c0, c1 = int(pairs.cue_off[b]), int(pairs.cue_off[b + 1])
+        jobs.append((pcm, pairs.cue_start[c0:c1], pairs.cue_end[c0:c1], list(ratios)))
+    t0 = time.perf_counter()
+    _CHECK_JOBS[:] = jobs
+    with mp.get_context("fork").Pool(min(len(jobs), max(1, (os.cpu_count() or 1)))) as pool:
+        res = pool.map(_oracle_check_worker, range(len(jobs)), chunksize=1)
+    _CHECK_JOBS[:] = []
+    bad, max_rel = [], 0.0
+    for b, (per_ratio, k) in zip(sample, res):
+        for kk, (sc, off) in enumerate(per_ratio):
+            rel = abs(a_score[b, kk] - sc) / max(abs(sc), 1.0)
+            max_rel = max(max_rel, rel)
+            if int(a_off[b, kk]) != int(off) or rel > 1e-5:
+                bad.append((b, kk, int(a_off[b, kk]), int(off), float(a_score[b, kk]), float(sc)))
+        sc, off = per_ratio[k]
+        if int(full["best_k"][b]) != k or int(full["best_offset"][b]) != int(off) \
+                or abs(full["best_score"][b] - sc) > 1e-5 * max(abs(sc), 1.0):
+            bad.append((b, "winner", int(full["best_k"][b]), k, int(full["best_offset"][b]), int(off)))
+    return {"ok": (not bad) and same_winner, "pairs_checked": sample, "ratios_checked": K,
+            "winner_only_equals_all_ratios": same_winner, "max_score_rel_err": max_rel,
+            "mismatches": bad[:8], "oracle_seconds": round(time.perf_counter() - t0, 1),
+            "what": "b2_sync_batch on the full batch vs oracle (numpy detector + complex128 FFTAligner + "
+                    "MaxScoreAligner) on a seeded sample; offsets exact, scores <= 1e-5 relative"}
+
+
+def measured_traffic():
+    """DRAM bytes per launch of the dominant kernel from this round's `ncu --set full` capture
+    (profiles/r2_vad_traffic.json, written by tools/ncu_traffic.py from the .ncu-rep)."""
+    p = os.path.join(ROOT, "profiles", "r2_vad_traffic.json")
+    if os.path.exists(p):
+        with open(p) as fh:
+            return json.load(fh)
+    return None
+
+
 def run_gpu(args):
     import torch
     from ffsubsync_b200 import _native, distributed
@@ -142,6 +233,7 @@ def run_gpu(args):
     from ffsubsync_b200.synth import BENCH_RATIOS, make_pairs
 
     rank, world, local_rank = distributed.init_from_env("nccl")
+    numa = distributed.bind_to_gpu_numa(local_rank)   # before any pinned allocation
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     ratios = BENCH_RATIOS[: args.ratios] if args.ratios <= len(BENCH_RATIOS) else None
@@ -150,13 +242,15 @@ def run_gpu(args):
         r = np.array(FRAMERATE_RATIOS)
         ratios = [1.0] + list(np.concatenate([r, 1.0 / r]))[: args.ratios - 1]
     K = len(ratios)
-    B = args.pairs                      # per GPU (weak scaling)
+    B = args.pairs if args.pairs else default_pairs(world)   # per GPU (weak scaling)
     bs = BatchSynchronizer(ratios, FRAME_RATE, SAMPLE_RATE, 0.0, max_offset_seconds=MAX_OFFSET_SECONDS,
                            device=local_rank)
     h = bs.handle
-    # everything (our kernels, torch ops, NCCL) is ordered on one explicit stream, and that is the
-    # stream the timing events are recorded on
+    # everything (our kernels, torch ops) is ordered on one explicit stream, and that is the stream
+    # the timing events are recorded on; the per-step NCCL gather runs on a side stream, ordered
+    # after the step's results by an event, so that step i+1 does not wait for it
     stream = torch.cuda.Stream(device=dev)
+    side = torch.cuda.Stream(device=dev)
     torch.cuda.set_stream(stream)
     bs.use_torch_stream()
 
@@ -172,52 +266,94 @@ def run_gpu(args):
     out = {"best_score": torch.empty(B, dtype=torch.float64, device=dev),
            "best_offset": torch.empty(B, dtype=torch.int32, device=dev),
            "best_k": torch.empty(B, dtype=torch.int32, device=dev)}
-    packed = torch.empty((B, 3), dtype=torch.float64, device=dev)
+    gather = world > 1 and not os.environ.get("B2_BENCH_NO_GATHER")  # the env knob is a diagnostic
+    packed = [torch.empty((B, 3), dtype=torch.float64, device=dev) for _ in range(2)]
+    packed_ev = [torch.cuda.Event(), torch.cuda.Event()]
+    gathered_ev = [None, None]
+    state = {"i": 0, "last": None}
 
     def step():
         bs.sync_device(pcm_d, pcm_off, pairs.cue_start, pairs.cue_end, pairs.cue_off, out=out)
-        if world > 1 and not os.environ.get("B2_BENCH_NO_GATHER"):  # the only exchange of the path: per-pair results to rank 0 (NCCL); the env knob is a diagnostic
-            packed[:, 0] = out["best_score"]
-            packed[:, 1] = out["best_offset"].to(torch.float64)
-            packed[:, 2] = out["best_k"].to(torch.float64)
-            return distributed.gather_pair_results(packed, B * world, rank, world)
-        return None
+        if not gather:
+            return
+        # the only exchange of the path: per-pair results to rank 0 (NCCL all-gather of 24 B/pair)
+        slot = state["i"] & 1
+        state["i"] += 1
+        if gathered_ev[slot] is not None:
+            stream.wait_event(gathered_ev[slot])      # the gather that last read this buffer is done
+        p = packed[slot]
+        p[:, 0] = out["best_score"]
+        p[:, 1] = out["best_offset"].to(torch.float64)
+        p[:, 2] = out["best_k"].to(torch.float64)
+        packed_ev[slot].record(stream)
+        with torch.cuda.stream(side):
+            side.wait_event(packed_ev[slot])
+            state["last"] = distributed.gather_pair_results(p, B * world, rank, world)
+            ev = torch.cuda.Event()
+            ev.record(side)
+            gathered_ev[slot] = ev
+
+    def drain():   # the caller's stream sees every gather before the end-of-region event
+        for ev in gathered_ev:
+            if ev is not None:
+                stream.wait_event(ev)
 
     for _ in range(args.warmup):
         step()
+    drain()
     torch.cuda.synchronize()
     ok = bool((out["best_offset"].cpu().numpy() == pairs.true_offset).all()
               and (out["best_k"].cpu().numpy() == pairs.true_k).all())
 
+    # ---- timed region ------------------------------------------------------------------------
+    # The clock sampler (NVML init + thread start: tens of ms, different on every rank) starts
+    # BEFORE the barrier; after the barrier only a stream synchronise separates the ranks from
+    # their start events, so no rank records ev0 early and then waits for the others inside
+    # its first collective.
     sampler = ClockSampler(local_rank)
-    if world > 1:
-        torch.distributed.barrier()
-    torch.cuda.synchronize()
     sampler.start()
+    steps = args.steps
     launches0 = h.launch_count
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda.synchronize()
+    if world > 1:
+        torch.distributed.barrier()
+    stream.synchronize()
     ev0.record(stream)
-    for _ in range(args.steps):
-        step()
+    t_wall = time.perf_counter()
+    done = 0
+    while True:
+        for _ in range(steps):
+            step()
+        done += steps
+        if not args.min_seconds or world > 1:
+            break
+        stream.synchronize()
+        if time.perf_counter() - t_wall >= args.min_seconds:
+            break
+    drain()
     ev1.record(stream)
     torch.cuda.synchronize()
     if world > 1:
         torch.distributed.barrier()
+    steps = done
     local_ms = ev0.elapsed_time(ev1)
     elapsed_ms = distributed.max_over_ranks(local_ms, dev)
     launches = h.launch_count - launches0
     clocks = sampler.stop()
     per_rank = None
     if world > 1:  # every rank's own device time and SM clock, for the record
-        mine = torch.tensor([local_ms / args.steps, float(clocks.get("sm_mhz") or 0.0)], dtype=torch.float64,
-                            device=dev)
-        allr = torch.empty((world, 2), dtype=torch.float64, device=dev)
+        mine = torch.tensor([local_ms / steps, float(clocks.get("sm_mhz") or 0.0),
+                             float(numa.get("node", -1))], dtype=torch.float64, device=dev)
+        allr = torch.empty((world, 3), dtype=torch.float64, device=dev)
         torch.distributed.all_gather_into_tensor(allr, mine)
-        per_rank = {"ms_per_step": [round(v, 4) for v in allr[:, 0].tolist()],
-                    "sm_mhz": allr[:, 1].tolist()}
+        ms = allr[:, 0].tolist()
+        per_rank = {"ms_per_step": [round(v, 4) for v in ms], "ms_min": round(min(ms), 4),
+                    "ms_max": round(max(ms), 4), "spread": round(max(ms) / min(ms) - 1.0, 4),
+                    "sm_mhz": allr[:, 1].tolist(), "numa_node": [int(v) for v in allr[:, 2].tolist()]}
 
     # ---- per-stage device times (CUDA events on the launching stream), rank 0 only -------------
-    stages, roofline, e2e, cpu_base = {}, None, None, None
+    stages, roofline, e2e, cpu_base, oracle_check = {}, None, None, None, None
     peak, peak_src = measured_peaks()
     if rank == 0:
         ref_off = pairs.win_off
@@ -251,14 +387,16 @@ def run_gpu(args):
                                              memspace=_native.B2_DEVICE), args.steps)
         stages = {"vad_ms": vad_ms, "rasterize_ms": ras_ms, "align_ms": ali_ms}
         achieved = BYTES_VAD * B / (vad_ms * 1e-3) / 1e9
-        # DRAM traffic per launch: ncu --set full capture of this kernel (profiles/r1j_ncu_summary.md,
-        # 16-pair launch): dram read+write = 3.7348 GB for 3.7325 GB of algorithmic bytes -> x1.0006
-        traffic_ratio = 1.0006
+        tr = measured_traffic()
+        traffic = traffic_src = None
+        if tr:
+            ratio = tr["dram_bytes_per_launch"] / float(tr["algorithmic_bytes_per_launch"])
+            traffic = BYTES_VAD * B * ratio
+            traffic_src = ("ncu --set full dram__bytes_read.sum + dram__bytes_write.sum of a %d-pair launch "
+                           "(%s), x%.4f of its algorithmic bytes, scaled to this launch's pairs"
+                           % (tr["pairs"], tr["source"], ratio))
         roofline = {"kernel": "vad_energy_zcr_kernel", "bound": "hbm", "achieved": achieved, "peak": peak,
-                    "unit": "GB/s", "frac": achieved / peak,
-                    "traffic": BYTES_VAD * B * traffic_ratio,
-                    "traffic_source": "ncu dram__bytes_read+write of a 16-pair launch (profiles/), scaled "
-                                      "by pairs; x%.4f of the algorithmic bytes" % traffic_ratio,
+                    "unit": "GB/s", "frac": achieved / peak, "traffic": traffic, "traffic_source": traffic_src,
                     "peak_source": peak_src,
                     "frac_note": "the peak is a COPY bandwidth (read+write mix); this kernel is 98.8 %% reads, "
                                  "which HBM3e serves faster than a copy - frac > 1 is not an error. Against the "
@@ -267,13 +405,16 @@ def run_gpu(args):
                     "stages_note": "stages_ms time b2_vad_energy_zcr / b2_rasterize / b2_align_batch called "
                                    "one by one; the timed step calls b2_sync_batch, which replaces the float "
                                    "rasteriser by bit masks (no rasterize_ms on that path)",
-                    "whole_path": {"achieved": (BYTES_VAD + bytes_align(K)) * B * args.steps
+                    "whole_path": {"achieved": (BYTES_VAD + bytes_align(K)) * B * steps
                                    / (elapsed_ms * 1e-3) / 1e9 if world == 1 else None,
                                    "unit": "GB/s (algorithmic bytes of VAD + align over the step time)"}}
         if roofline["whole_path"]["achieved"]:
             roofline["whole_path"]["frac"] = roofline["whole_path"]["achieved"] / peak
-        del ref_sig, sub_sig
+        del ref_sig, sub_sig, sc, of, st
 
+        if not args.no_oracle_check:
+            oracle_check = verify_against_oracle(bs, pairs, pcm_d, pcm_off, ratios, args.oracle_pairs, 2024 + B)
+            ok = ok and oracle_check["ok"]
         if world == 1 and not args.no_cpu_baseline:
             cpu_base = cpu_baseline_sample(K, ratios, budget_pairs=None)
 
@@ -297,27 +438,38 @@ def run_gpu(args):
     e_s = distributed.max_over_ranks((time.perf_counter() - t0) / args.steps * 1e3, dev) / 1e3
     ok_e = distributed.max_over_ranks(0.0 if bool((res[1] == pairs.true_offset[:Be]).all()) else 1.0, dev) == 0.0
     ok = ok and ok_e
+    h2d = int(n_e * 2 + cue_hi * 16 + (Be + 1) * 16 + K * 8)
     e2e = {"value": Be * world / e_s, "unit": UNIT, "pairs_per_step": Be * world,
-           "h2d_bytes_per_step": int(n_e * 2 + cue_hi * 16 + (Be + 1) * 16 + K * 8) * world,
+           "h2d_bytes_per_step": h2d * world,
            "d2h_bytes_per_step": int(Be * 16) * world, "ms_per_step": e_s * 1e3,
-           "note": "b2_sync_batch with B2_HOST buffers on every rank (own PCIe link each), max over "
-                   "ranks; PCIe H2D of the PCM is the bound"}
+           "h2d_gbs_per_gpu": h2d / e_s / 1e9, "numa": numa,
+           "note": "b2_sync_batch with B2_HOST buffers on every rank (own PCIe link each, rank bound to its "
+                   "GPU's NUMA node before the pinned allocation), max over ranks; PCIe H2D of the PCM is "
+                   "the bound"}
     del pcm_h
 
     if rank == 0:
-        total_pairs = B * world * args.steps
+        total_pairs = B * world * steps
+        cfg_name = ("BASELINE configs[3]: 4096 two-hour pairs sharded over 8 GPUs (512 per GPU)"
+                    if (world == 8 and B == 512) else
+                    "BASELINE configs[2]: batch of 256 two-hour pairs per GPU" if B == 256 else
+                    "batch of %d two-hour pairs per GPU (BASELINE configs[2] workload at another batch size)" % B)
         line = {
             "metric": METRIC, "value": total_pairs / (elapsed_ms * 1e-3), "unit": UNIT, "n_gpus": world,
-            "steps": args.steps, "warmup": args.warmup, "ms_per_step": elapsed_ms / args.steps,
+            "steps": steps, "warmup": args.warmup, "ms_per_step": elapsed_ms / steps,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "int64 VAD; f32 FFT nomination + f64 exact re-score", "data": "synthetic",
-            "config": {"workload": "BASELINE configs[2] with the VAD of configs[1]: batch of 2 h pairs per GPU, "
-                                   "16 kHz mono s16le PCM -> energy/ZCR VAD -> MaxScoreAligner over K ratios, "
-                                   "max_offset_seconds=60", "pairs_per_gpu": B, "ratios": K,
+            "config": {"workload": cfg_name + ", with the VAD of configs[1]: 16 kHz mono s16le PCM -> energy/ZCR "
+                                   "VAD -> MaxScoreAligner over K ratios, max_offset_seconds=60",
+                       "pairs_per_gpu": B, "ratios": K,
                        "signal_frames": 720000, "pcm_samples_per_pair": 115200000,
                        "l2_policy": "inputs (%.1f GB PCM per GPU) are far larger than the 126 MB L2"
-                                    % (B * 0.2304), "parallelism": "pairs block-sharded, dp%d" % world},
-            "verified_offsets": ok, "gpu_launches": int(launches), "clocks": clocks, "per_rank": per_rank, "stages_ms": stages,
+                                    % (B * 0.2304), "parallelism": "pairs block-sharded, dp%d" % world,
+                       "exchange": ("NCCL all_gather_into_tensor of 24 B/pair per step on a side stream "
+                                    "(event-ordered after the step's results)") if gather else None},
+            "verified_offsets": ok, "verified_vs_oracle": oracle_check, "gpu_launches": int(launches),
+            "clocks": clocks, "per_rank": per_rank, "stages_ms": stages,
+            "timed_region_s": elapsed_ms * 1e-3,
             "roofline": roofline, "e2e": e2e, "cpu_baseline": cpu_base,
         }
         print(json.dumps(line))
@@ -439,9 +591,15 @@ def main():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--pairs", type=int, default=int(os.environ.get("B2_BENCH_PAIRS", "148")),
-                    help="2 h pairs per GPU per step (default: one per SM, so that pairs x ratios "
-                         "correlation jobs fill whole waves of 148 CTAs; 34 GB of PCM per GPU)")
+    ap.add_argument("--pairs", type=int, default=0,
+                    help="2 h pairs per GPU per step (default: BASELINE configs[2] = 256 on 1/2/4 GPUs, "
+                         "configs[3] = 512 per GPU on 8 GPUs; 59 / 118 GB of PCM per GPU)")
+    ap.add_argument("--min-seconds", type=float, default=0.0,
+                    help="1 GPU only: repeat the K timed steps until the timed region is at least this long "
+                         "(sustained-clock runs for profiles/; `steps` in the output is what actually ran)")
+    ap.add_argument("--oracle-pairs", type=int, default=8,
+                    help="pairs of the batch cross-checked against the oracle after the timed region")
+    ap.add_argument("--no-oracle-check", action="store_true")
     ap.add_argument("--ratios", type=int, default=5)
     ap.add_argument("--e2e-pairs", type=int, default=4)
     ap.add_argument("--no-cpu-baseline", action="store_true")

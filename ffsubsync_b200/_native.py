@@ -14,7 +14,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "_lib", "libffsubsync_b200.so")
 
 B2_HOST, B2_DEVICE = 0, 1
-B2_MAX_OFFSET_NONE = -1
+B2_MAX_OFFSET_NONE = -(1 << 63)   # INT64_MIN: FFTAligner(max_offset_samples=None)
 ALIGN_OK, ALIGN_EMPTY, ALIGN_ALL_MASKED, ALIGN_CAND_OVERFLOW = 0, 1, 2, 4
 STATUS_NAMES = {0: "B2_OK", -1: "B2_ERR_BAD_ARG", -2: "B2_ERR_CUDA", -3: "B2_ERR_EMPTY_INPUT",
                 -4: "B2_ERR_NO_ALIGNMENT", -5: "B2_ERR_NOMEM", -6: "B2_ERR_UNSUPPORTED"}
@@ -25,7 +25,8 @@ EXPORTS = [
     "b2_launch_count", "b2_vad_frames_per_window", "b2_vad_num_windows", "b2_vad_energy_zcr",
     "b2_rasterize_lengths", "b2_rasterize", "b2_blend_signals", "b2_first_last_nonzero", "b2_align_batch",
     "b2_reduce_ratios", "b2_sync_batch", "b2_synth_pcm", "b2_vad_stream_begin", "b2_vad_stream_push",
-    "b2_vad_stream_windows", "b2_vad_stream_end",
+    "b2_vad_stream_windows", "b2_vad_stream_end", "b2_auditok_block_size", "b2_auditok_energy_floor",
+    "b2_vad_auditok",
 ]
 
 
@@ -74,13 +75,13 @@ def load() -> ctypes.CDLL:
                                      ctypes.c_int, _vp, ctypes.c_int, _f64, _vp, _vp, ctypes.c_int]
         lib.b2_first_last_nonzero.argtypes = [_vp, _vp, _vp, ctypes.c_int, _vp, _vp, ctypes.c_int]
         lib.b2_blend_signals.argtypes = [_vp, _vp, _vp, _i64, ctypes.c_int, _f64, _f64, _vp, ctypes.c_int]
-        lib.b2_align_batch.argtypes = [_vp, _vp, _vp, _vp, _vp, ctypes.c_int, ctypes.c_int, _i32,
+        lib.b2_align_batch.argtypes = [_vp, _vp, _vp, _vp, _vp, ctypes.c_int, ctypes.c_int, _i64,
                                        _vp, _vp, _vp, ctypes.c_int]
-        lib.b2_reduce_ratios.argtypes = [_vp, _vp, _vp, _vp, ctypes.c_int, ctypes.c_int, _i32,
+        lib.b2_reduce_ratios.argtypes = [_vp, _vp, _vp, _vp, ctypes.c_int, ctypes.c_int, _i64,
                                          _vp, _vp, _vp, ctypes.c_int]
         lib.b2_sync_batch.argtypes = [_vp, _vp, _vp, ctypes.c_int, ctypes.c_int, ctypes.c_int, _f32,
                                       _i64, ctypes.c_int, ctypes.c_int, _vp, _vp, _vp, _vp, _vp,
-                                      ctypes.c_int, _f64, _i32, _vp, _vp, _vp, _vp, _vp, ctypes.c_int]
+                                      ctypes.c_int, _f64, _i64, _vp, _vp, _vp, _vp, _vp, ctypes.c_int]
         lib.b2_synth_pcm.argtypes = [_vp, _vp, _i64, ctypes.c_int, ctypes.c_uint32, _vp, ctypes.c_int]
         lib.b2_vad_stream_begin.argtypes = [_vp, ctypes.c_int, ctypes.c_int, _f32, _i64, ctypes.c_int,
                                             ctypes.c_int]
@@ -88,6 +89,11 @@ def load() -> ctypes.CDLL:
         lib.b2_vad_stream_windows.argtypes = [_vp]
         lib.b2_vad_stream_windows.restype = _i64
         lib.b2_vad_stream_end.argtypes = [_vp, _vp, _i64, ctypes.POINTER(_i64)]
+        lib.b2_auditok_block_size.argtypes = [ctypes.c_int, ctypes.c_int]
+        lib.b2_auditok_energy_floor.argtypes = [ctypes.c_int, _f64]
+        lib.b2_auditok_energy_floor.restype = _i64
+        lib.b2_vad_auditok.argtypes = [_vp, _vp, _vp, ctypes.c_int, ctypes.c_int, ctypes.c_int, _f64, _f64,
+                                       _f64, _i64, _f64, _i64, _vp, _vp, ctypes.c_int]
         _lib = lib
         return lib
 
@@ -99,6 +105,16 @@ def _ptr(a) -> Optional[int]:
     if isinstance(a, int):
         return a
     return a.ctypes.data
+
+
+def _mask_width(max_offset_samples) -> int:
+    """None -> B2_MAX_OFFSET_NONE; any Python int -> an int64 the library feeds to the reference's
+    slice arithmetic (aligners.py:31-43).  Widths beyond +-2^62 behave like every width larger
+    than the padded length, so clamping them keeps the result and avoids ctypes wrap-around."""
+    if max_offset_samples is None:
+        return B2_MAX_OFFSET_NONE
+    lim = 1 << 62
+    return max(-lim, min(lim, int(max_offset_samples)))
 
 
 def _i64a(x) -> np.ndarray:
@@ -170,6 +186,37 @@ class Handle:
                                         float(non_speech_label), int(energy_threshold), int(z_lo),
                                         int(z_hi), _ptr(out), _ptr(out_off), memspace)
         self._check(st, "b2_vad_energy_zcr")
+        return out, out_off
+
+    def vad_auditok(self, pcm, pcm_off, frame_rate: int, sample_rate: int, non_speech_label: float,
+                    energy_threshold_db: float = 50.0, min_length: Optional[float] = None,
+                    max_length: Optional[int] = None, max_continuous_silence: Optional[float] = None,
+                    chunk_samples: int = 0, out=None, memspace: int = B2_HOST):
+        """auditok detector over B signals (b2_vad_auditok); tokenizer defaults are the reference's
+        (speech_transformers.py:126-131).  Returns (float64 per block, out_off[B+1])."""
+        pcm_off = _i64a(pcm_off)
+        B = len(pcm_off) - 1
+        fpw = int(self.lib.b2_auditok_block_size(frame_rate, sample_rate))
+        if fpw <= 0:
+            raise ValueError("auditok detector: unsupported frame_rate=%r / sample_rate=%r" % (frame_rate, sample_rate))
+        min_length = 0.2 * sample_rate if min_length is None else min_length
+        max_length = int(5 * sample_rate) if max_length is None else max_length
+        max_continuous_silence = 0.25 * sample_rate if max_continuous_silence is None else max_continuous_silence
+        n = np.diff(pcm_off)
+        if chunk_samples > 0:
+            full, rem = n // chunk_samples, n % chunk_samples
+            nwin = full * ((chunk_samples + fpw - 1) // fpw) + (rem + fpw - 1) // fpw
+        else:
+            nwin = (n + fpw - 1) // fpw
+        out_off = np.concatenate([[0], np.cumsum(nwin)]).astype(np.int64)
+        if memspace == B2_HOST:
+            pcm = np.ascontiguousarray(pcm, dtype=np.int16)
+            out = np.empty(int(out_off[-1]), dtype=np.float64)
+        st = self.lib.b2_vad_auditok(self.h, _ptr(pcm), _ptr(pcm_off), B, frame_rate, sample_rate,
+                                     float(non_speech_label), float(energy_threshold_db), float(min_length),
+                                     int(max_length), float(max_continuous_silence), int(chunk_samples),
+                                     _ptr(out), _ptr(out_off), memspace)
+        self._check(st, "b2_vad_auditok")
         return out, out_off
 
     # streaming detector (b2_vad_stream_*): push() returns before the chunk is processed
@@ -272,7 +319,7 @@ class Handle:
     def align_batch(self, ref, ref_off, sub, sub_off, B: int, K: int, max_offset_samples: Optional[int],
                     score=None, offset=None, status=None, memspace: int = B2_HOST):
         ref_off, sub_off = _i64a(ref_off), _i64a(sub_off)
-        mos = B2_MAX_OFFSET_NONE if max_offset_samples is None else int(max_offset_samples)
+        mos = _mask_width(max_offset_samples)
         if memspace == B2_HOST:
             ref = np.ascontiguousarray(ref, dtype=np.float32)
             sub = np.ascontiguousarray(sub, dtype=np.float32)
@@ -286,7 +333,7 @@ class Handle:
 
     def reduce_ratios(self, score, offset, status, B: int, K: int, max_offset_samples: Optional[int],
                       best_score=None, best_offset=None, best_k=None, memspace: int = B2_HOST):
-        mos = B2_MAX_OFFSET_NONE if max_offset_samples is None else int(max_offset_samples)
+        mos = _mask_width(max_offset_samples)
         if memspace == B2_HOST:
             score = np.ascontiguousarray(score, dtype=np.float64)
             offset = np.ascontiguousarray(offset, dtype=np.int32)
@@ -311,7 +358,7 @@ class Handle:
         cue_start_s = np.ascontiguousarray(cue_start_s, dtype=np.float64)
         cue_end_s = np.ascontiguousarray(cue_end_s, dtype=np.float64)
         cue_keep = None if cue_keep is None else np.ascontiguousarray(cue_keep, dtype=np.uint8)
-        mos = B2_MAX_OFFSET_NONE if max_offset_samples is None else int(max_offset_samples)
+        mos = _mask_width(max_offset_samples)
         if memspace == B2_HOST:
             pcm = np.ascontiguousarray(pcm, dtype=np.int16)
             best_score = np.empty(B, dtype=np.float64)
@@ -330,10 +377,27 @@ class Handle:
         return best_score, best_offset, best_k, all_score, all_offset
 
 
+def _default_device() -> int:
+    """The device a handle is created on when the caller names none: torch's current CUDA device
+    when torch is loaded and has a CUDA context (so kernels launch where the caller's ``.cuda()``
+    tensors live, also on rank > 0), else LOCAL_RANK when B2_DEVICE_FROM_RANK is set, else 0."""
+    import sys
+    torch = sys.modules.get("torch")
+    if torch is not None:
+        try:
+            if torch.cuda.is_available() and torch.cuda.is_initialized():
+                return int(torch.cuda.current_device())
+        except Exception:
+            pass
+    if os.environ.get("B2_DEVICE_FROM_RANK"):
+        return int(os.environ.get("LOCAL_RANK", "0"))
+    return 0
+
+
 def get_handle(device: Optional[int] = None) -> Handle:
     """Per-thread handle (the reference runs several VideoSpeechTransformer.fit on threads)."""
     if device is None:
-        device = int(os.environ.get("LOCAL_RANK", "0")) if os.environ.get("B2_DEVICE_FROM_RANK") else 0
+        device = _default_device()
     handles = getattr(_tls, "handles", None)
     if handles is None:
         handles = _tls.handles = {}

@@ -8,7 +8,20 @@
 
 #include "common.cuh"
 
-extern "C" int b2_version(void) { return 100; }
+// Entry guard: the handle's device is current for the duration of the call and the caller
+// thread's previous device is restored on every return path.
+struct DeviceScope {
+  int prev = -1, want;
+  bool ok = true;
+  explicit DeviceScope(int dev) : want(dev) {
+    if (cudaGetDevice(&prev) != cudaSuccess) prev = -1;
+    if (prev != want) ok = cudaSetDevice(want) == cudaSuccess;
+  }
+  ~DeviceScope() {
+    if (prev >= 0 && prev != want) cudaSetDevice(prev);
+  }
+};
+extern "C" int b2_version(void) { return 200; }
 
 static uint64_t compute_log2_quirk_mask() {
   // CPython: total_bits = math.log(n, 2) == log(n)/log(2) in double; ceil() of that is k+1 for
@@ -29,7 +42,8 @@ extern "C" int b2_create(int device, b2_handle* out) {
     return B2_ERR_CUDA;
   b2_ctx* h = new b2_ctx();
   h->device = device;
-  if (cudaSetDevice(device) != cudaSuccess) { delete h; return B2_ERR_CUDA; }
+  DeviceScope scope(device);
+  if (!scope.ok) { delete h; return B2_ERR_CUDA; }
   cudaDeviceProp prop;
   if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) { delete h; return B2_ERR_CUDA; }
   h->sm_count = prop.multiProcessorCount;
@@ -61,7 +75,7 @@ extern "C" int b2_create(int device, b2_handle* out) {
 
 extern "C" int b2_destroy(b2_handle h) {
   if (!h) return B2_OK;
-  cudaSetDevice(h->device);
+  DeviceScope scope(h->device);
   cudaStreamSynchronize(h->stream);
   for (auto& w : h->ws)
     if (w.p) cudaFree(w.p);
@@ -91,7 +105,7 @@ extern "C" int b2_destroy(b2_handle h) {
 
 extern "C" int b2_set_stream(b2_handle h, void* s) {
   if (!h) return B2_ERR_BAD_ARG;
-  cudaSetDevice(h->device);
+  DeviceScope scope(h->device);
   if (h->own_stream && h->stream) {
     cudaStreamSynchronize(h->stream);
     cudaStreamDestroy(h->stream);
@@ -108,6 +122,7 @@ extern "C" int b2_set_stream(b2_handle h, void* s) {
 
 extern "C" int b2_synchronize(b2_handle h) {
   if (!h) return B2_ERR_BAD_ARG;
+  DeviceScope scope(h->device);
   B2_CUDA(h, cudaStreamSynchronize(h->stream));
   return B2_OK;
 }
@@ -257,7 +272,27 @@ static int copy_out(b2_ctx* h, void* host, const void* dev, size_t bytes) {
 #define B2_ENTER(h)                                   \
   if (!(h)) return B2_ERR_BAD_ARG;                    \
   (h)->err.clear();                                   \
-  if (cudaSetDevice((h)->device) != cudaSuccess) return B2_ERR_CUDA;
+  DeviceScope _b2_scope((h)->device);                 \
+  if (!_b2_scope.ok) return B2_ERR_CUDA;
+
+// B2_DEVICE calls: a bulk pointer must be device (or managed) memory of the handle's device.
+static int check_device_ptr(b2_ctx* h, const void* p, const char* what) {
+  if (!p) return B2_OK;
+  cudaPointerAttributes at;
+  if (cudaPointerGetAttributes(&at, p) != cudaSuccess) {
+    cudaGetLastError();
+    B2_FAIL(h, B2_ERR_BAD_ARG, "%s: not a CUDA pointer", what);
+  }
+  if (at.type == cudaMemoryTypeManaged) return B2_OK;
+  if (at.type != cudaMemoryTypeDevice)
+    B2_FAIL(h, B2_ERR_BAD_ARG, "%s: B2_DEVICE call with a host pointer", what);
+  if (at.device != h->device)
+    B2_FAIL(h, B2_ERR_BAD_ARG, "%s: pointer lives on device %d, the handle on device %d", what, at.device,
+            h->device);
+  return B2_OK;
+}
+#define B2_CHECK_DEV(h, memspace, p, what) \
+  if ((memspace) == B2_DEVICE) B2_TRY(check_device_ptr(h, p, what))
 
 // ---- VAD -----------------------------------------------------------------------------------
 extern "C" int b2_vad_frames_per_window(int frame_rate, int sample_rate) {
@@ -292,6 +327,8 @@ extern "C" int b2_vad_energy_zcr(b2_handle h, const int16_t* pcm, const int64_t*
   if (B == 0) return B2_OK;
   int64_t n_total = pcm_off[B], w_total = out_off[B];
   if ((n_total && !pcm) || (w_total && !out)) B2_FAIL(h, B2_ERR_BAD_ARG, "vad: null data pointer");
+  B2_CHECK_DEV(h, memspace, pcm, "vad: pcm");
+  B2_CHECK_DEV(h, memspace, out, "vad: out");
   const int16_t* d_pcm = pcm;
   float* d_out = out;
   if (memspace == B2_HOST) {
@@ -301,10 +338,111 @@ extern "C" int b2_vad_energy_zcr(b2_handle h, const int16_t* pcm, const int64_t*
     d_pcm = (const int16_t*)dp;
     d_out = (float*)dq;
   }
-  B2_TRY(b2i_vad_launch(h, d_pcm, pcm_off, B, fpw, non_speech_label, energy_threshold, z_lo, z_hi,
-                        d_out, out_off));
+  B2_TRY(b2i_vad_launch(h, d_pcm, pcm_off, B, fpw, non_speech_label, (int64_t)fpw * energy_threshold,
+                        z_lo, z_hi, d_out, out_off));
   if (memspace == B2_HOST) {
     B2_TRY(copy_out(h, out, d_out, (size_t)w_total * 4));
+    B2_CUDA(h, cudaStreamSynchronize(h->stream));
+  }
+  return B2_OK;
+}
+
+// ---- auditok detector (speech_transformers.py:101-152) ---------------------------------------
+extern "C" int b2_auditok_block_size(int frame_rate, int sample_rate) {
+  if (frame_rate <= 0 || sample_rate <= 0) return 0;
+  // ADSFactory.ads(block_dur=1.0/sample_rate): int(sampling_rate * block_dur), speech_transformers.py:140;
+  // the output length formula uses frame_rate // sample_rate (:122,143-145): the two must agree
+  volatile double dur = 1.0 / (double)sample_rate;
+  volatile double prod = (double)frame_rate * dur;
+  const int block = (int)prod;
+  return block == frame_rate / sample_rate ? block : 0;
+}
+
+extern "C" int64_t b2_auditok_energy_floor(int n_samples, double energy_threshold_db) {
+  // smallest integer sum of squares E with 10*log10(E/n) >= threshold, evaluated with the same
+  // float64 expression auditok's AudioEnergyValidator uses (log energy -200 for E = 0)
+  if (n_samples <= 0) return INT64_MAX;
+  if (-200.0 >= energy_threshold_db) return 0;
+  auto valid = [&](int64_t e) {
+    volatile double energy = (double)e / (double)n_samples;
+    volatile double le = 10.0 * log10(energy);
+    return le >= energy_threshold_db;
+  };
+  const double guess = (double)n_samples * pow(10.0, energy_threshold_db / 10.0);
+  const double e_max = (double)n_samples * 32768.0 * 32768.0;   // int16 blocks cannot exceed this
+  if (!(guess <= 2.0 * e_max)) return INT64_MAX;
+  int64_t lo = 0, hi = (int64_t)guess + 1;                       // !valid(0) holds: log energy -200
+  while (!valid(hi)) {
+    if ((double)hi > 4.0 * e_max) return INT64_MAX;
+    hi *= 2;
+  }
+  while (hi - lo > 1) {
+    const int64_t mid = lo + (hi - lo) / 2;
+    if (valid(mid)) hi = mid;
+    else lo = mid;
+  }
+  return hi;
+}
+
+extern "C" int b2_vad_auditok(b2_handle h, const int16_t* pcm, const int64_t* pcm_off, int B,
+                              int frame_rate, int sample_rate, double non_speech_label,
+                              double energy_threshold_db, double min_length, int64_t max_length,
+                              double max_continuous_silence, int64_t chunk_samples, double* out,
+                              const int64_t* out_off, int memspace) {
+  B2_ENTER(h);
+  if (B < 0 || !pcm_off || !out_off) B2_FAIL(h, B2_ERR_BAD_ARG, "auditok: null offset table / B<0");
+  const int fpw = b2_auditok_block_size(frame_rate, sample_rate);
+  if (fpw <= 0)
+    B2_FAIL(h, B2_ERR_UNSUPPORTED, "auditok: int(frame_rate/sample_rate) block size and frame_rate//sample_rate "
+                                   "window size differ (or are 0) for %d / %d", frame_rate, sample_rate);
+  // StreamTokenizer.__init__ argument checks
+  if (max_length <= 0 || !(min_length > 0) || min_length > (double)max_length ||
+      !(max_continuous_silence < (double)max_length) || chunk_samples < 0)
+    B2_FAIL(h, B2_ERR_BAD_ARG, "auditok: bad tokenizer parameters");
+  // one detector call per chunk: chunk c of signal b becomes "signal" n of the batched energy kernel
+  std::vector<int64_t> c_pcm(1, 0), c_out(1, 0), tail;
+  for (int b = 0; b < B; ++b) {
+    const int64_t n = pcm_off[b + 1] - pcm_off[b];
+    if (n < 0) B2_FAIL(h, B2_ERR_BAD_ARG, "auditok: pcm_off not monotone at %d", b);
+    if (c_pcm.back() != pcm_off[b] - pcm_off[0])
+      B2_FAIL(h, B2_ERR_BAD_ARG, "auditok: internal chunk table mismatch");
+    int64_t nwin = 0;
+    const int64_t step = chunk_samples > 0 ? chunk_samples : (n > 0 ? n : 1);
+    for (int64_t s = 0; s < n; s += step) {
+      const int64_t len = std::min(step, n - s);
+      const int64_t w = (len + fpw - 1) / fpw;
+      c_pcm.push_back(c_pcm.back() + len);
+      c_out.push_back(c_out.back() + w);
+      const int rem = (int)(len % fpw);
+      tail.push_back(rem ? b2_auditok_energy_floor(rem, energy_threshold_db) : 0);
+      nwin += w;
+    }
+    if (out_off[b + 1] - out_off[b] != nwin)
+      B2_FAIL(h, B2_ERR_BAD_ARG, "auditok: out_off[%d] span must be the sum of ceil(chunk/fpw)", b);
+  }
+  const int n_chunks = (int)tail.size();
+  if (n_chunks == 0) return B2_OK;
+  const int64_t n_total = pcm_off[B] - pcm_off[0], w_total = c_out.back();
+  if ((n_total && !pcm) || (w_total && !out)) B2_FAIL(h, B2_ERR_BAD_ARG, "auditok: null data pointer");
+  B2_CHECK_DEV(h, memspace, pcm, "auditok: pcm");
+  B2_CHECK_DEV(h, memspace, out, "auditok: out");
+  const int16_t* d_pcm = pcm + pcm_off[0];
+  double* d_out = out + out_off[0];
+  void *d_flags, *dp, *dq;
+  if (memspace == B2_HOST) {
+    B2_TRY(stage_in(h, b2_ctx::WS_STAGE_IN0, pcm + pcm_off[0], (size_t)n_total * 2, &dp));
+    B2_TRY(b2i_ws(h, b2_ctx::WS_STAGE_OUT, (size_t)w_total * 8 + 16, &dq));
+    d_pcm = (const int16_t*)dp;
+    d_out = (double*)dq;
+  }
+  B2_TRY(b2i_ws(h, b2_ctx::WS_SIG_REF, (size_t)w_total * 4 + 64, &d_flags));
+  B2_TRY(b2i_vad_launch(h, d_pcm, c_pcm.data(), n_chunks, fpw, 0.0f,
+                        b2_auditok_energy_floor(fpw, energy_threshold_db), 0, fpw, (float*)d_flags,
+                        c_out.data(), tail.data()));
+  B2TokenizerParams tp{min_length, max_continuous_silence, non_speech_label, (long long)max_length};
+  B2_TRY(b2i_tokenize_launch(h, (const float*)d_flags, c_out.data(), n_chunks, tp, d_out));
+  if (memspace == B2_HOST) {
+    B2_TRY(copy_out(h, out + out_off[0], d_out, (size_t)w_total * 8));
     B2_CUDA(h, cudaStreamSynchronize(h->stream));
   }
   return B2_OK;
@@ -375,8 +513,8 @@ extern "C" int b2_vad_stream_push(b2_handle h, const void* pcm_bytes, int64_t n_
   memcpy(sl.hp, pcm_bytes, (size_t)n * 2);
   B2_CUDA(h, cudaMemcpyAsync(sl.dp, sl.hp, (size_t)n * 2, cudaMemcpyHostToDevice, h->stream));
   const int64_t pcm_off[2] = {0, n}, out_off[2] = {0, nwin};
-  B2_TRY(b2i_vad_launch(h, (const int16_t*)sl.dp, pcm_off, 1, vs.fpw, vs.label, vs.thr, vs.z_lo, vs.z_hi,
-                        sl.dout, out_off));
+  B2_TRY(b2i_vad_launch(h, (const int16_t*)sl.dp, pcm_off, 1, vs.fpw, vs.label, (int64_t)vs.fpw * vs.thr,
+                        vs.z_lo, vs.z_hi, sl.dout, out_off));
   B2_CUDA(h, cudaMemcpyAsync(sl.hout, sl.dout, (size_t)nwin * 4, cudaMemcpyDeviceToHost, h->stream));
   B2_CUDA(h, cudaEventRecord(sl.ev, h->stream));
   sl.n_out = nwin;
@@ -553,15 +691,16 @@ extern "C" int b2_first_last_nonzero(b2_handle h, const float* sig, const int64_
 // ---- aligner -------------------------------------------------------------------------------
 extern "C" int b2_align_batch(b2_handle h, const float* ref, const int64_t* ref_off,
                               const float* sub, const int64_t* sub_off, int B, int K,
-                              int32_t max_offset_samples, double* score, int32_t* offset,
+                              int64_t max_offset_samples, double* score, int32_t* offset,
                               int32_t* status, int memspace) {
   B2_ENTER(h);
   if (B < 0 || K < 0 || !ref_off || !sub_off) B2_FAIL(h, B2_ERR_BAD_ARG, "align: bad arguments");
-  if (max_offset_samples < B2_MAX_OFFSET_NONE)
-    B2_FAIL(h, B2_ERR_BAD_ARG, "align: max_offset_samples must be >= 0 or B2_MAX_OFFSET_NONE");
   if (B == 0 || K == 0) return B2_OK;
   if (!score || !offset || !status) B2_FAIL(h, B2_ERR_BAD_ARG, "align: null output");
   size_t J = (size_t)B * K;
+  B2_CHECK_DEV(h, memspace, ref, "align: ref");
+  B2_CHECK_DEV(h, memspace, sub, "align: sub");
+  B2_CHECK_DEV(h, memspace, score, "align: score");
   const float *d_ref = ref, *d_sub = sub;
   double* d_score = score;
   int32_t *d_offset = offset, *d_status = status;
@@ -588,7 +727,7 @@ extern "C" int b2_align_batch(b2_handle h, const float* ref, const int64_t* ref_
 }
 
 extern "C" int b2_reduce_ratios(b2_handle h, const double* score, const int32_t* offset,
-                                const int32_t* status, int B, int K, int32_t max_offset_samples,
+                                const int32_t* status, int B, int K, int64_t max_offset_samples,
                                 double* best_score, int32_t* best_offset, int32_t* best_k,
                                 int memspace) {
   B2_ENTER(h);
@@ -637,10 +776,11 @@ extern "C" int b2_sync_batch(b2_handle h, const int16_t* pcm, const int64_t* pcm
                              int64_t energy_threshold, int z_lo, int z_hi,
                              const double* cue_start_s, const double* cue_end_s,
                              const uint8_t* cue_keep, const int64_t* cue_off, const double* ratios,
-                             int K, double start_seconds, int32_t max_offset_samples,
+                             int K, double start_seconds, int64_t max_offset_samples,
                              double* best_score, int32_t* best_offset, int32_t* best_k,
                              double* all_score, int32_t* all_offset, int memspace) {
   B2_ENTER(h);
+  B2Range range("b2_sync_batch");
   if (B < 0 || K <= 0 || !pcm_off || !cue_off || !ratios)
     B2_FAIL(h, B2_ERR_BAD_ARG, "sync_batch: bad arguments");
   if (B == 0) return B2_OK;
@@ -681,6 +821,8 @@ extern "C" int b2_sync_batch(b2_handle h, const int16_t* pcm, const int64_t* pcm
   int32_t* d_bo = d_status + J;
   int32_t* d_bk = d_bo + B;
 
+  B2_CHECK_DEV(h, memspace, pcm, "sync_batch: pcm");
+  B2_CHECK_DEV(h, memspace, best_score, "sync_batch: best_score");
   const int16_t* d_pcm = pcm;
   if (memspace == B2_HOST) {
     void* dp;
@@ -720,7 +862,7 @@ extern "C" int b2_sync_batch(b2_handle h, const int16_t* pcm, const int64_t* pcm
       const char* vc = getenv("B2_VAD_CTAS");
       h->vad_ctas_per_sm = (n_sub > 1 && i > 0) ? (vc ? atoi(vc) : 1) : 0;
       const int st = b2i_vad_launch(h, d_pcm, pcm_off + b0, nb, fpw, non_speech_label,
-                                    energy_threshold, z_lo, z_hi, (float*)d_refsig,
+                                    (int64_t)fpw * energy_threshold, z_lo, z_hi, (float*)d_refsig,
                                     ref_off.data() + b0);
       h->vad_ctas_per_sm = 0;
       if (st != B2_OK) return st;

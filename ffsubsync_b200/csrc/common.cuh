@@ -10,7 +10,16 @@
 #include <string>
 #include <vector>
 
+#include <nvtx3/nvToolsExt.h>
+
 #include "../../include/ffsubsync_b200.h"
+
+// NVTX range per stage (header-only nvtx3: a no-op costing one pointer test unless a profiler is
+// attached).  Shows up in ncu / nsys timelines as vad / raster_bits / ref_spectra+correlate / ...
+struct B2Range {
+  explicit B2Range(const char* name) { nvtxRangePushA(name); }
+  ~B2Range() { nvtxRangePop(); }
+};
 
 struct DeviceBuf {
   void* p = nullptr;
@@ -126,9 +135,19 @@ int b2i_meta_commit(MetaArena* a);
 static inline int64_t ceil_div64(int64_t a, int64_t b) { return (a + b - 1) / b; }
 
 // ---- kernels' host launchers (defined in the .cu files) ------------------------------------
+// e_min_full: smallest sum of squares of a full window that is speech.  tail_emin_host (nullable,
+// [B]): evaluate each signal's trailing partial window against its own floor (auditok contract);
+// null = partial windows are non-speech (webrtc contract).
 int b2i_vad_launch(b2_ctx* h, const int16_t* d_pcm, const int64_t* pcm_off_host, int B, int fpw,
-                   float non_speech_label, int64_t energy_threshold, int z_lo, int z_hi,
-                   float* d_out, const int64_t* out_off_host);
+                   float non_speech_label, int64_t e_min_full, int z_lo, int z_hi,
+                   float* d_out, const int64_t* out_off_host, const int64_t* tail_emin_host = nullptr);
+struct B2TokenizerParams {
+  double min_length, max_continuous_silence, non_speech_label;
+  long long max_length;
+};
+// flags / out share the offset table off_host[n_chunks + 1] (one detector call per chunk)
+int b2i_tokenize_launch(b2_ctx* h, const float* d_flags, const int64_t* off_host, int n_chunks,
+                        const B2TokenizerParams& tp, double* d_out);
 int b2i_synth_launch(b2_ctx* h, const uint8_t* d_cls, int64_t n_windows, int fpw, uint32_t seed,
                      int16_t* d_out);
 int b2i_raster_launch(b2_ctx* h, const double* cue_start, const double* cue_end,
@@ -155,8 +174,8 @@ int b2i_raster_bits_launch(b2_ctx* h, const B2CueSource* src, int B, int K, cons
                            const long long* bits_off, uint32_t* d_bits);
 int b2i_align_launch(b2_ctx* h, const float* d_ref, const int64_t* ref_off_host,
                      const float* d_sub, const int64_t* sub_off_host, int B, int K,
-                     int32_t max_offset_samples, double* d_score, int32_t* d_offset,
+                     int64_t max_offset_samples, double* d_score, int32_t* d_offset,
                      int32_t* d_status, int winner_only, const B2CueSource* cue_src);
 int b2i_reduce_launch(b2_ctx* h, const double* d_score, const int32_t* d_offset,
-                      const int32_t* d_status, int B, int K, int32_t max_offset_samples,
+                      const int32_t* d_status, int B, int K, int64_t max_offset_samples,
                       double* d_best_score, int32_t* d_best_offset, int32_t* d_best_k);

@@ -634,9 +634,10 @@ long long floor_div(long long a, long long b) {
 }  // namespace
 
 int b2i_align_launch(b2_ctx* h, const float* d_ref, const int64_t* ref_off, const float* d_sub,
-                     const int64_t* sub_off, int B, int K, int32_t max_offset_samples,
+                     const int64_t* sub_off, int B, int K, int64_t max_offset_samples,
                      double* d_score, int32_t* d_offset, int32_t* d_status, int winner_only,
                      const B2CueSource* cue_src) {
+  B2Range range("b2:align (ref_spectra, sub_correlate, select, rescore, pick)");
   const size_t J = (size_t)B * K;
   // cue mode (b2_sync_batch): the subtitle signals exist only as bit masks, rasterised from the cue
   // list by raster_bits_kernel below (sub_off then only carries the signal lengths)
@@ -675,9 +676,12 @@ int b2i_align_launch(b2_ctx* h, const float* d_ref, const int64_t* ref_off, cons
       }
       const long long N = padded_length(h, R + S);
       long long lo = 0, hi = N;  // surviving index range, aligners.py:31-43 with slice semantics
-      if (max_offset_samples >= 0) {
-        const long long a = N - 1 - max_offset_samples - S;
-        const long long bb = N - 1 + (long long)max_offset_samples - S;
+      if (max_offset_samples != B2_MAX_OFFSET_NONE) {
+        // any int64 width, negative ones included, through the reference's slice arithmetic; widths
+        // are clamped to +-2^40 first (beyond every padded length, so the result is unchanged)
+        const long long mo = std::max<long long>(-(1LL << 40), std::min<long long>(1LL << 40, max_offset_samples));
+        const long long a = N - 1 - mo - S;
+        const long long bb = N - 1 + mo - S;
         lo = a >= 0 ? std::min(a, N) : std::max(a + N, 0LL);
         hi = bb >= 0 ? std::min(bb, N) : std::max(bb + N, 0LL);
       }
@@ -867,6 +871,7 @@ int b2i_align_launch(b2_ctx* h, const float* d_ref, const int64_t* ref_off, cons
   }
   B2_TRY(flush());
 
+  B2Range range_sel("b2:select+rescore+pick");
   MetaArena a;
   B2_TRY(b2i_meta_begin(h, &a, J * sizeof(SelJob) + 256));
   const SelJob* d_sel = (const SelJob*)b2i_meta_put(&a, sel.data(), J * sizeof(SelJob));

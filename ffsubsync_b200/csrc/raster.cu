@@ -133,7 +133,7 @@ __global__ void __launch_bounds__(256) bounds_kernel(const float* __restrict__ s
 __global__ void __launch_bounds__(128) reduce_ratios_kernel(const double* __restrict__ score,
                                                              const int32_t* __restrict__ offset,
                                                              const int32_t* __restrict__ status,
-                                                             int B, int K, int max_off,
+                                                             int B, int K, long long max_off,
                                                              double* __restrict__ best_score,
                                                              int32_t* __restrict__ best_offset,
                                                              int32_t* __restrict__ best_k) {
@@ -146,7 +146,7 @@ __global__ void __launch_bounds__(128) reduce_ratios_kernel(const double* __rest
     const size_t j = (size_t)b * K + k;
     if (status && (status[j] & B2_ALIGN_EMPTY)) continue;  // FFTAligner.fit raised for this one
     const int o = offset[j];
-    if (max_off >= 0 && abs(o) > max_off) continue;
+    if (max_off != B2_MAX_OFFSET_NONE && llabs((long long)o) > max_off) continue;
     const double s = score[j];
     if (bk < 0 || s > bs) {
       bk = k;
@@ -189,6 +189,7 @@ int b2i_raster_launch(b2_ctx* h, const double* cue_start, const double* cue_end,
                       const uint8_t* cue_keep, const int64_t* cue_off, int B, const double* ratios,
                       int K, int per_pair_ratios, const double* levels, int sample_rate,
                       double start_seconds, float* d_out, const int64_t* out_off) {
+  B2Range range("b2:rasterize");
   // cue_off / out_off may be slices of larger tables (sub-batches): entries are absolute indices
   // into cue_start/... and d_out, only [cue_off[0], cue_off[B]) is uploaded (pointers rebased)
   const size_t J = (size_t)B * K;
@@ -228,6 +229,7 @@ int b2i_raster_launch(b2_ctx* h, const double* cue_start, const double* cue_end,
 
 int b2i_raster_bits_launch(b2_ctx* h, const B2CueSource* src, int B, int K, const int64_t* sig_off,
                            const long long* bits_off, uint32_t* d_bits) {
+  B2Range range("b2:raster_bits");
   // cue_off / sig_off may be slices of larger tables (sub-batches), see b2i_raster_launch
   const size_t J = (size_t)B * K;
   const size_t c0 = (size_t)src->cue_off[0], nc = (size_t)src->cue_off[B] - c0;
@@ -271,10 +273,11 @@ int b2i_bounds_launch(b2_ctx* h, const float* d_sig, const int64_t* off_host, in
 }
 
 int b2i_reduce_launch(b2_ctx* h, const double* d_score, const int32_t* d_offset,
-                      const int32_t* d_status, int B, int K, int32_t max_offset_samples,
+                      const int32_t* d_status, int B, int K, int64_t max_offset_samples,
                       double* d_best_score, int32_t* d_best_offset, int32_t* d_best_k) {
+  B2Range range("b2:reduce_ratios");
   reduce_ratios_kernel<<<(B + 127) / 128, 128, 0, h->stream>>>(
-      d_score, d_offset, d_status, B, K, max_offset_samples, d_best_score, d_best_offset, d_best_k);
+      d_score, d_offset, d_status, B, K, (long long)max_offset_samples, d_best_score, d_best_offset, d_best_k);
   B2_CHECK_LAUNCH(h, "reduce_ratios_kernel");
   return B2_OK;
 }

@@ -27,6 +27,7 @@ struct TileDesc {
   long long n_left;     // samples of the signal from the tile's first sample to the signal end
   long long span_gbyte; // global byte offset of the staged span start
   int n_windows;        // windows in this tile (0 = no more tiles for this CTA)
+  int sig;              // index of the signal the tile belongs to
   int head_bytes;       // offset of the first sample inside the 16 B-aligned staged span
   int tail_src_off;     // >=0: bytes [tail_src_off, tail_end) of the span must be copied by hand
   int tail_end;
@@ -41,7 +42,11 @@ struct VadParams {
   unsigned long long* tile_counter;  // zeroed before the launch
   long long total_tiles;
   long long pcm_total_bytes;
-  long long e_min;            // fpw * energy_threshold
+  long long e_min;            // smallest sum of squares of a full window that counts as speech
+  // auditok contract (b2_vad_auditok): a trailing partial window of signal b is evaluated on the
+  // samples it has, speech <=> sum x^2 >= tail_emin[b] (no zero-crossing band).  nullptr: the
+  // webrtc contract - a partial window is non-speech.
+  const long long* tail_emin;
   int B, fpw, G, tw, z_lo, z_hi, fast, stage_bytes, cpl, stages;
   float label;
 };
@@ -170,11 +175,19 @@ __device__ __forceinline__ void consume_tile_fast(const VadParams& p, const Tile
     long long e = 0;
     int z = 0;
     const bool active = wl < d.n_windows;
-    const bool full = active && d.n_left - (long long)wl * fpw >= fpw;
-    if (full) window_part_fast<CPL>(span + (size_t)wl * fpw * 2, g, p.cpl, e, z);
+    const long long avail = d.n_left - (long long)wl * fpw;
+    const bool full = active && avail >= fpw;
+    const bool tail = active && !full && avail > 0 && p.tail_emin != nullptr;
+    if (full) {
+      window_part_fast<CPL>(span + (size_t)wl * fpw * 2, g, p.cpl, e, z);
+    } else if (tail) {  // at most one window per signal: plain 16-bit loop over the samples it has
+      const short* xs = reinterpret_cast<const short*>(span + (size_t)wl * fpw * 2);
+      for (int i = g; i < (int)avail; i += p.G) e += (long long)xs[i] * xs[i];
+    }
     lane_group_sum<GT>(p.G, e, z);
     if (active && g == 0) {
-      const bool speech = full && e >= p.e_min && z >= p.z_lo && z <= p.z_hi;
+      const bool speech = full ? (e >= p.e_min && z >= p.z_lo && z <= p.z_hi)
+                               : (tail && e >= p.tail_emin[d.sig]);
       p.out[d.out_base + wl] = speech ? 1.0f : p.label;
     }
   }
@@ -215,6 +228,7 @@ __global__ void __launch_bounds__(kThreads) vad_energy_zcr_kernel(VadParams p) {
       TileDesc d;
       if (t >= p.total_tiles) {
         d.n_windows = 0;
+        d.sig = 0;
         d.out_base = d.n_left = d.span_gbyte = 0;
         d.head_bytes = 0;
         d.tail_src_off = -1;
@@ -237,6 +251,7 @@ __global__ void __launch_bounds__(kThreads) vad_energy_zcr_kernel(VadParams p) {
       const long long bulk_end = min(a1, limit);
       const uint32_t bulk = bulk_end > a0 ? (uint32_t)(bulk_end - a0) : 0u;
       d.n_windows = nw;
+      d.sig = cur_b;
       d.out_base = p.out_off[cur_b] + w0;
       d.n_left = sig1 - s0;
       d.head_bytes = (int)(b0 - a0);
@@ -285,10 +300,13 @@ __global__ void __launch_bounds__(kThreads) vad_energy_zcr_kernel(VadParams p) {
         long long e = 0;
         int z = 0;
         const bool active = wl < d.n_windows;
-        const bool full = active && d.n_left - (long long)wl * fpw >= fpw;
-        if (full) {
+        const long long avail = d.n_left - (long long)wl * fpw;
+        const bool full = active && avail >= fpw;
+        const bool tail = active && !full && avail > 0 && p.tail_emin != nullptr;
+        if (full || tail) {
           const short* xs = reinterpret_cast<const short*>(span + d.head_bytes + (size_t)wl * fpw * 2);
-          for (int i = g; i < fpw; i += G) {
+          const int n_use = full ? fpw : (int)avail;
+          for (int i = g; i < n_use; i += G) {
             const int x = xs[i];
             const int px = i > 0 ? (int)xs[i - 1] : x;
             e += (long long)x * x;
@@ -297,7 +315,8 @@ __global__ void __launch_bounds__(kThreads) vad_energy_zcr_kernel(VadParams p) {
         }
         lane_group_sum<0>(G, e, z);
         if (active && g == 0) {
-          const bool speech = full && e >= p.e_min && z >= p.z_lo && z <= p.z_hi;
+          const bool speech = full ? (e >= p.e_min && z >= p.z_lo && z <= p.z_hi)
+                                   : (tail && e >= p.tail_emin[d.sig]);
           p.out[d.out_base + wl] = speech ? 1.0f : p.label;
         }
       }
@@ -354,8 +373,9 @@ int b2i_synth_launch(b2_ctx* h, const uint8_t* d_cls, int64_t n_windows, int fpw
 }
 
 int b2i_vad_launch(b2_ctx* h, const int16_t* d_pcm, const int64_t* pcm_off, int B, int fpw,
-                   float non_speech_label, int64_t energy_threshold, int z_lo, int z_hi,
-                   float* d_out, const int64_t* out_off) {
+                   float non_speech_label, int64_t e_min_full, int z_lo, int z_hi,
+                   float* d_out, const int64_t* out_off, const int64_t* tail_emin) {
+  B2Range range("b2:vad_energy_zcr");
   if (((uintptr_t)d_pcm & 15) != 0)
     B2_FAIL(h, B2_ERR_BAD_ARG, "vad: device PCM pointer must be 16-byte aligned");
   VadParams p;
@@ -418,17 +438,18 @@ int b2i_vad_launch(b2_ctx* h, const int16_t* d_pcm, const int64_t* pcm_off, int 
 
   MetaArena a;
   size_t tbl = (size_t)(B + 1) * 8;
-  B2_TRY(b2i_meta_begin(h, &a, 3 * tbl + 256));
+  B2_TRY(b2i_meta_begin(h, &a, 4 * tbl + 256));
   p.pcm_off = (const long long*)b2i_meta_put(&a, pcm_off, tbl);
   p.out_off = (const long long*)b2i_meta_put(&a, out_off, tbl);
   p.tile_off = (const long long*)b2i_meta_put(&a, tile_off.data(), tbl);
+  p.tail_emin = tail_emin ? (const long long*)b2i_meta_put(&a, tail_emin, (size_t)B * 8) : nullptr;
   B2_TRY(b2i_meta_commit(&a));
 
   p.pcm_bytes = (const unsigned char*)d_pcm;
   p.out = d_out;
   p.B = B;
   p.pcm_total_bytes = 2 * (long long)pcm_off[B];
-  p.e_min = (long long)fpw * (long long)energy_threshold;
+  p.e_min = (long long)e_min_full;
   p.z_lo = z_lo;
   p.z_hi = z_hi;
   p.label = non_speech_label;

@@ -34,6 +34,59 @@ def init_from_env(backend: Optional[str] = None) -> Tuple[int, int, int]:
     return rank, world, local_rank
 
 
+def _parse_cpulist(text: str) -> set:
+    cpus = set()
+    for part in text.strip().split(","):
+        if not part:
+            continue
+        lo, _, hi = part.partition("-")
+        cpus.update(range(int(lo), int(hi or lo) + 1))
+    return cpus
+
+
+def gpu_numa_node(device_index: int) -> Tuple[int, str]:
+    """(NUMA node of the GPU's PCIe root, PCI bus id) from sysfs; node -1 when unknown."""
+    bus = None
+    try:
+        p = torch.cuda.get_device_properties(device_index)
+        bus = "%04x:%02x:%02x.0" % (p.pci_domain_id, p.pci_bus_id, p.pci_device_id)
+    except Exception:
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            info = pynvml.nvmlDeviceGetPciInfo(pynvml.nvmlDeviceGetHandleByIndex(device_index))
+            raw = info.busId.decode() if isinstance(info.busId, bytes) else info.busId
+            bus = raw.lower()[-12:]
+        except Exception:
+            return -1, ""
+    try:
+        with open("/sys/bus/pci/devices/%s/numa_node" % bus) as fh:
+            return int(fh.read().strip()), bus
+    except (OSError, ValueError):
+        return -1, bus
+
+
+def bind_to_gpu_numa(local_rank: int) -> dict:
+    """Pin this process to the CPU cores of its GPU's NUMA node (call before allocating pinned host
+    buffers: first touch then places them on that node, so H2D copies do not cross the socket
+    interconnect).  Returns what was done, for the bench record; never raises."""
+    info = {"node": -1, "bound": False}
+    try:
+        node, bus = gpu_numa_node(local_rank)
+        info.update(node=node, pci=bus)
+        if node < 0:
+            return info
+        with open("/sys/devices/system/node/node%d/cpulist" % node) as fh:
+            cpus = _parse_cpulist(fh.read())
+        allowed = os.sched_getaffinity(0) & cpus
+        if allowed:
+            os.sched_setaffinity(0, allowed)
+            info.update(bound=True, cpus=len(allowed))
+    except Exception as e:  # containers may hide sysfs or forbid sched_setaffinity
+        info["error"] = str(e)
+    return info
+
+
 def shard_pairs(n_pairs: int, rank: int, world: int) -> Tuple[int, int]:
     """Block sharding: rank g owns pairs [g*B/G, (g+1)*B/G)."""
     return (rank * n_pairs) // world, ((rank + 1) * n_pairs) // world

@@ -10,8 +10,11 @@
   * ``MultiSegmentVideoSpeechTransformer`` (:760-903) - sparse reference from a few sampled
     windows; the windows of an in-memory / raw-PCM reference go through ONE batched VAD launch.
 
-Out of scope here: embedded-subtitle extraction, silero/webrtc/auditok
-detectors (third-party wheels).  Other detectors can be plugged in through
+  * ``_make_auditok_detector`` (:101-152) - the reference's auditok detector, energy test +
+    StreamTokenizer + impulses/cumsum/clip, on the GPU (no auditok wheel needed).
+
+Out of scope here: embedded-subtitle extraction, silero / webrtc detectors
+(third-party wheels / model weights).  Other detectors can be plugged in through
 ``DETECTOR_FACTORIES`` with the reference's factory signature.
 """
 import io
@@ -104,8 +107,34 @@ def _make_energy_detector(sample_rate: int, frame_rate: int, non_speech_label: f
     return _make_energy_zcr_detector(sample_rate, frame_rate, non_speech_label, z_lo=0, z_hi=fpw)
 
 
+def _make_auditok_detector(
+    sample_rate: int, frame_rate: int, non_speech_label: float
+) -> Callable[[Union[bytes, np.ndarray]], np.ndarray]:
+    """The reference's auditok detector (speech_transformers.py:101-152) without the auditok wheel:
+    energy test per 10 ms block (``AudioEnergyValidator(sample_width=2, energy_threshold=50)``, :125),
+    ``StreamTokenizer(min_length=0.2*sample_rate, max_length=5*sample_rate,
+    max_continuous_silence=0.25*sample_rate)`` (:126-131), start / end+1 impulses -> cumsum -> clip
+    (:146-150) - all on the GPU (b2_vad_auditok: the energy kernel + a per-call tokenizer scan).
+    One call = one chunk; like the reference's tokenizer the state restarts in every call."""
+    handle = _native.get_handle()
+    if handle.lib.b2_auditok_block_size(frame_rate, sample_rate) <= 0:
+        raise ValueError("auditok detector: unsupported frame_rate=%r / sample_rate=%r" % (frame_rate, sample_rate))
+
+    def _detect(asegment) -> np.ndarray:
+        raw = np.frombuffer(asegment, dtype=np.uint8) if not isinstance(asegment, np.ndarray) \
+            else np.ascontiguousarray(asegment).view(np.uint8)
+        if len(raw) % 2 != 0:  # auditok's BufferAudioSource refuses such a buffer
+            raise ValueError("length of data_buffer must be a multiple of (sample_width * channels)")
+        pcm = raw.view("<i2")
+        out, _ = _native.get_handle().vad_auditok(pcm, [0, len(pcm)], frame_rate, sample_rate, non_speech_label)
+        return out
+
+    return _detect
+
+
 #: name fragment looked up in ``VideoSpeechTransformer.vad`` -> factory(sample_rate, frame_rate, label)
 DETECTOR_FACTORIES: Dict[str, Callable[[int, int, float], Callable]] = {
+    "auditok": _make_auditok_detector,
     "energy_only": _make_energy_detector,
     "energy": _make_energy_zcr_detector,
 }
@@ -454,7 +483,8 @@ class MultiSegmentVideoSpeechTransformer(TransformerMixin):
     def _extract_all_batched(self, fname, starts: List[int], band) -> Dict[int, np.ndarray]:
         """All windows of a raw-PCM reference in one VAD launch."""
         if isinstance(fname, str):
-            pcm_all = np.memmap(fname, dtype="<i2", mode="r")
+            raw = np.memmap(fname, dtype=np.uint8, mode="r")   # an odd trailing byte is ignored
+            pcm_all = raw[: (len(raw) // 2) * 2].view("<i2")
         elif isinstance(fname, np.ndarray):
             raw = np.ascontiguousarray(fname).view(np.uint8)
             pcm_all = raw[: (len(raw) // 2) * 2].view("<i2")
@@ -593,15 +623,31 @@ class DeserializeSpeechTransformer(TransformerMixin):
 
 
 def make_subtitle_speech_pipeline(
-    parser,
+    fmt: str = "srt",
+    encoding: str = "infer",
+    caching: bool = False,
+    max_subtitle_seconds: int = 10,
     start_seconds: int = DEFAULT_START_SECONDS,
     scale_factor: Optional[float] = DEFAULT_SCALE_FACTOR,
-    **_ignored,
+    parser=None,
+    **kwargs,
 ) -> Union[Pipeline, Callable[[float], Pipeline]]:
-    """parse -> scale -> speech_extract, or (scale_factor=None) a maker ``ratio -> Pipeline`` for
-    the golden-section search.  Subtitle *parsing* is outside the hot path, so ``parser`` (any
-    transformer whose ``transform`` yields cues) must be supplied by the caller; the reference
-    builds one from a file format (speech_transformers.py:56-98)."""
+    """parse -> scale -> speech_extract, or (``scale_factor=None``) a maker ``ratio -> Pipeline`` for
+    the golden-section search; same positional order and keywords as the reference
+    (speech_transformers.py:56-98).  Subtitle *parsing* is outside the hot path,
+    so where the reference would build a parser from ``fmt`` / ``encoding`` / ... the caller must
+    pass ``parser=`` (any transformer whose ``transform`` yields cues with ``.start`` / ``.end`` /
+    ``.content``); a parser that carries ``encoding`` / ``max_subtitle_seconds`` / ``start_seconds``
+    attributes is checked against the arguments like the reference does (:73-75)."""
+    if parser is None:
+        raise ValueError(
+            "make_subtitle_speech_pipeline(fmt=%r, ...): subtitle parsing is not part of this package; "
+            "pass parser=<transformer yielding cues> (the reference builds one with "
+            "make_subtitle_parser here)" % (fmt,))
+    for name, want in (("encoding", encoding), ("max_subtitle_seconds", max_subtitle_seconds),
+                       ("start_seconds", start_seconds)):
+        if hasattr(parser, name):
+            assert getattr(parser, name) == want, "parser.%s != %r" % (name, want)
 
     def subpipe_maker(framerate_ratio):
         return Pipeline([

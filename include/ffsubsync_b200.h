@@ -11,8 +11,10 @@
  *   - every function returns B2_OK (0) or a negative b2_status; b2_last_error(h) gives text.
  *   - "memspace" says where the BULK arrays of that call live: B2_HOST (the library stages
  *     them through pinned memory, copies results back and synchronises before returning) or
- *     B2_DEVICE (pointers are device pointers on the handle's device; the call only enqueues
- *     work on the handle's stream and does not synchronise).
+ *     B2_DEVICE (pointers are device pointers on the handle's device - a pointer that belongs to
+ *     another device is rejected with B2_ERR_BAD_ARG; the call only enqueues work on the handle's
+ *     stream and does not synchronise).  Calls leave the caller thread's current CUDA device as
+ *     they found it.
  *   - METADATA arrays (offset tables "*_off", cue lists, ratio lists) are always host pointers.
  *   - offset tables have n+1 entries, in elements (not bytes): item i is [off[i], off[i+1]).
  *   - a handle owns its stream/workspace and is not thread-safe; use one handle per thread
@@ -52,7 +54,10 @@ enum {
                          the pair's best, so it was not re-scored; fp32 score / its argmax kept */
 };
 
-#define B2_MAX_OFFSET_NONE (-1) /* FFTAligner(max_offset_samples=None) */
+/* FFTAligner(max_offset_samples=None).  Every other int64 value is a mask width and goes through the
+ * reference's slice arithmetic (ffsubsync/aligners.py:31-43) literally - negative widths mask
+ * everything (score -inf, offset N-1-S), widths beyond the padded length mask nothing. */
+#define B2_MAX_OFFSET_NONE INT64_MIN
 
 /* ---- lifecycle ----------------------------------------------------------------------- */
 int b2_version(void);
@@ -93,6 +98,27 @@ int b2_vad_stream_push(b2_handle h, const void* pcm_bytes, int64_t n_bytes);
 int64_t b2_vad_stream_windows(b2_handle h);
 int b2_vad_stream_end(b2_handle h, float* out, int64_t capacity, int64_t* n_out);
 
+/* ---- auditok detector: replaces _make_auditok_detector._detect ------------------------------
+ * ffsubsync/speech_transformers.py:101-152.  The third-party arithmetic (auditok==0.1.5, absent from
+ * the image) is restated from its published algorithm in oracle/auditok_oracle.py:
+ *   energy test per 10 ms block (AudioEnergyValidator, :125): 10*log10(sum x^2 / n) >= energy_threshold_db,
+ *     evaluated as  sum x^2 >= b2_auditok_energy_floor(n, energy_threshold_db)  (integer-exact; a
+ *     trailing shorter block is tested on the samples it has);
+ *   StreamTokenizer(min_length, max_length, max_continuous_silence) (:126-131) over the block flags;
+ *   start / end+1 impulses, float64 cumsum, clip to [0, 1] (:146-150).
+ * Each signal is cut into detector calls of chunk_samples samples (0 = one call per signal; the
+ * reference's chunk loop uses 100 s, :710-746) and the tokenizer restarts in every call (:142).
+ * out: float64 per block, ceil(chunk/fpw) per call, fpw = frame_rate // sample_rate; out_off[b] spans
+ * the blocks of signal b.  pcm/out follow memspace.  B2_ERR_UNSUPPORTED when auditok's block size
+ * int(frame_rate * (1/sample_rate)) differs from frame_rate // sample_rate. */
+int b2_auditok_block_size(int frame_rate, int sample_rate);
+int64_t b2_auditok_energy_floor(int n_samples, double energy_threshold_db);
+int b2_vad_auditok(b2_handle h, const int16_t* pcm, const int64_t* pcm_off, int B,
+                   int frame_rate, int sample_rate, double non_speech_label,
+                   double energy_threshold_db, double min_length, int64_t max_length,
+                   double max_continuous_silence, int64_t chunk_samples,
+                   double* out, const int64_t* out_off, int memspace);
+
 /* ---- subtitle side: replaces SubtitleScaler.fit + SubtitleSpeechTransformer.fit ----------
  * ffsubsync/subtitle_transformers.py:35-47 and ffsubsync/speech_transformers.py:957-980.
  * Cues (seconds, float64, unscaled) of pair b are [cue_off[b], cue_off[b+1]); keep[i]==0 for
@@ -131,7 +157,7 @@ int b2_first_last_nonzero(b2_handle h, const float* sig, const int64_t* sig_off,
  * score/offset/status follow memspace like the signals. */
 int b2_align_batch(b2_handle h, const float* ref, const int64_t* ref_off /* [B+1] */,
                    const float* sub, const int64_t* sub_off /* [B*K+1] */, int B, int K,
-                   int32_t max_offset_samples,
+                   int64_t max_offset_samples,
                    double* score, int32_t* offset, int32_t* status, int memspace);
 
 /* ---- MaxScoreAligner.transform over the K candidates of each pair -------------------------
@@ -139,7 +165,7 @@ int b2_align_batch(b2_handle h, const float* ref, const int64_t* ref_off /* [B+1
  * list order wins ties.  best_k[b] = -1 when nothing survives (-> B2_ERR_NO_ALIGNMENT in the
  * single-pair wrappers). */
 int b2_reduce_ratios(b2_handle h, const double* score, const int32_t* offset,
-                     const int32_t* status, int B, int K, int32_t max_offset_samples,
+                     const int32_t* status, int B, int K, int64_t max_offset_samples,
                      double* best_score, int32_t* best_offset, int32_t* best_k, int memspace);
 
 /* ---- the whole hot path for a batch of (video, subtitle) pairs -----------------------------
@@ -150,7 +176,7 @@ int b2_sync_batch(b2_handle h, const int16_t* pcm, const int64_t* pcm_off, int B
                   int64_t energy_threshold, int z_lo, int z_hi,
                   const double* cue_start_s, const double* cue_end_s, const uint8_t* cue_keep,
                   const int64_t* cue_off, const double* ratios, int K, double start_seconds,
-                  int32_t max_offset_samples,
+                  int64_t max_offset_samples,
                   double* best_score, int32_t* best_offset, int32_t* best_k,
                   double* all_score /* [B*K] or NULL */, int32_t* all_offset /* or NULL */,
                   int memspace);

@@ -735,3 +735,161 @@ def test_sync_two_hour_pair_recovers_offset(handle):
             del os.environ["B2_ALIGN_SPLIT"]
         assert np.array_equal(r[0], bs) and np.array_equal(r[1], bo) and np.array_equal(r[2], bk)
         assert np.array_equal(r[3], a_s) and np.array_equal(r[4], a_o), split
+
+
+# ============================================================== auditok detector (V3) on the GPU
+
+def _auditok_pcm(rng, frame_rate, n_blocks, cut=0):
+    """PCM whose per-block energies straddle the 50 dB edge, in runs that exercise the tokenizer:
+    blips shorter than min_length, silences around max_continuous_silence = 25, runs beyond
+    max_length = 500."""
+    fpw = frame_rate // 100
+    runs = []
+    while sum(runs) < n_blocks:
+        runs.append(int(rng.choice([1, 3, 8, 19, 20, 21, 24, 25, 26, 27, 60, 150, 499, 500, 501, 700])))
+    amp = np.concatenate([np.full(r, 1.12 if (i % 2 == 0) else 0.88) for i, r in enumerate(runs)])[:n_blocks]
+    amp = amp * rng.uniform(0.9, 1.1, len(amp))     # decisions flip near the edge inside the runs too
+    pcm = np.round(rng.randn(n_blocks * fpw) * 316.2 * np.repeat(amp, fpw)).astype(np.int16)
+    return pcm[: len(pcm) - cut] if cut else pcm
+
+
+@pytest.mark.parametrize("frame_rate", [16000, 48000, 44100, 8000])
+@pytest.mark.parametrize("label", [0.0, 0.3])
+def test_auditok_detector_matches_oracle(handle, frame_rate, label):
+    from ffsubsync_b200.speech_transformers import _make_auditok_detector
+    from oracle import auditok_oracle as au
+    rng = np.random.RandomState(frame_rate % 89 + int(label * 10))
+    det = _make_auditok_detector(100, frame_rate, label)
+    fpw = frame_rate // 100
+    for n_blocks, cut in ((6000, 0), (2500, 13), (700, fpw - 1), (30, 1), (1, 0)):
+        pcm = _auditok_pcm(rng, frame_rate, n_blocks, cut)
+        want = au.auditok_detect_fast(pcm.tobytes(), 100, frame_rate, label)
+        got = det(np.frombuffer(pcm.tobytes(), np.uint8))
+        assert got.dtype == np.float64 and len(got) == len(want)
+        assert np.array_equal(got, want), (frame_rate, label, n_blocks, cut, int(np.argmax(got != want)))
+        assert 0 < want.sum()
+    assert len(det(b"")) == 0
+    with pytest.raises(ValueError):
+        det(b"\x01\x02\x03")
+    # the literal (per-block numpy validator) restatement on a shorter input
+    pcm = _auditok_pcm(rng, frame_rate, 1200, 5)
+    assert np.array_equal(det(pcm.tobytes()), au.auditok_detect(pcm.tobytes(), 100, frame_rate, label))
+
+
+def test_energy_rule_equals_the_auditok_validator(handle):
+    """The per-window energy decision of this package's detectors (E >= fpw * 10^5) is auditok's
+    AudioEnergyValidator(energy_threshold=50) on the same block - the pin for the VAD arithmetic."""
+    from ffsubsync_b200.speech_transformers import _make_energy_detector
+    from oracle import auditok_oracle as au
+    rng = np.random.RandomState(17)
+    for frame_rate in (16000, 48000):
+        fpw = frame_rate // 100
+        pcm = _auditok_pcm(rng, frame_rate, 3000)
+        # exact-edge blocks: E == fpw * 10^5 (valid) and one LSB below (invalid)
+        edge = np.zeros(fpw, np.int16)
+        edge[: fpw * 10 // 16] = 400                    # (10/16) fpw * 160000 = fpw * 10^5
+        pcm[:fpw] = edge
+        edge[0] = 399
+        pcm[fpw:2 * fpw] = edge
+        got = _make_energy_detector(100, frame_rate, 0.0)(pcm.tobytes())
+        want = np.array([1.0 if au.block_is_valid(b, 50) else 0.0 for b in au.read_blocks(pcm, fpw)])
+        assert np.array_equal(got, want) and got[0] == 1.0 and got[1] == 0.0
+        assert 0.2 < want.mean() < 0.8
+
+
+def test_auditok_chunk_loop_250s(handle):
+    """VideoSpeechTransformer(vad='auditok') over 250 s: three detector calls (100 + 100 + 50 s), the
+    tokenizer restarting in each (speech_transformers.py:142,746)."""
+    from ffsubsync_b200.speech_transformers import VideoSpeechTransformer
+    from oracle import auditok_oracle as au
+    rng = np.random.RandomState(250)
+    pcm = _auditok_pcm(rng, 16000, 25000, cut=77)
+    for label in (0.0, 0.5):
+        vst = VideoSpeechTransformer("auditok", 100, 16000, label).fit(pcm.tobytes())
+        chunk = 160 * 10000
+        want = np.concatenate([au.auditok_detect_fast(pcm[i:i + chunk].tobytes(), 100, 16000, label)
+                               for i in range(0, len(pcm), chunk)])
+        assert np.array_equal(vst.transform(), want)
+        # restarting matters: one call over the whole buffer gives a different signal
+        assert not np.array_equal(want, au.auditok_detect_fast(pcm.tobytes(), 100, 16000, label))
+
+
+def test_auditok_batch_abi_chunked(handle):
+    from oracle import auditok_oracle as au
+    rng = np.random.RandomState(99)
+    sigs = [_auditok_pcm(rng, 16000, n, cut) for n, cut in ((23000, 0), (10000, 159), (1, 0), (12000, 8))]
+    sigs.insert(2, np.zeros(0, np.int16))
+    off = np.concatenate([[0], np.cumsum([len(s) for s in sigs])])
+    chunk = 160 * 10000
+    out, out_off = handle.vad_auditok(np.concatenate(sigs), off, 16000, 100, 0.0, chunk_samples=chunk)
+    for b, s in enumerate(sigs):
+        want = [au.auditok_detect_fast(s[i:i + chunk].tobytes(), 100, 16000, 0.0) for i in range(0, len(s), chunk)]
+        want = np.concatenate(want) if want else np.zeros(0)
+        assert np.array_equal(out[out_off[b]:out_off[b + 1]], want), b
+    # other tokenizer parameters / threshold through the ABI
+    out, _ = handle.vad_auditok(sigs[0], [0, len(sigs[0])], 16000, 100, 0.0, energy_threshold_db=49.0,
+                                min_length=3, max_length=40, max_continuous_silence=0)
+    fl = (sigs[0].astype(np.int64).reshape(-1, 160) ** 2).sum(axis=1) >= au.energy_floor(160, 49.0)
+    m = np.zeros(len(fl) + 1)
+    for s, e in au.tokenize(list(fl), 3, 40, 0):
+        m[s] = 1.0
+        m[e + 1] = -1.0
+    assert np.array_equal(out, np.clip(np.cumsum(m)[:-1], 0, 1))
+
+
+# ============================================================ ABI corner cases (round-1 advice)
+
+def test_mask_width_corner_cases(handle):
+    """Any integer mask width goes through the reference's slice arithmetic: negative widths mask
+    everything (score -inf, offset N-1-S), huge widths mask nothing."""
+    from ffsubsync_b200.aligners import FFTAligner
+    rng = np.random.RandomState(4)
+    ref = (rng.rand(500) > 0.5).astype(float)
+    sub = np.concatenate([np.zeros(17), ref])[:480]
+    for mos in (-1, -7, -10 ** 6, 0, 1, 2 ** 31, 2 ** 40, 2 ** 70):
+        got = FFTAligner(max_offset_samples=mos).fit_transform(ref, sub, get_score=True)
+        want = ao.fft_align(ref, sub, mos)
+        assert got[1] == want[1] and _score_ok(got[0], want[0]), (mos, got, want)
+    assert FFTAligner(max_offset_samples=-1).fit_transform(ref, sub, get_score=True)[0] == -np.inf
+
+
+def test_device_calls_reject_host_pointers(handle):
+    from ffsubsync_b200 import _native
+    pcm = np.zeros(1600, np.int16)
+    out = np.zeros(10, np.float32)
+    with pytest.raises(_native.NativeError):
+        handle.vad_energy_zcr(pcm.ctypes.data, [0, 1600], 16000, 100, 0.0, 100000, out=out.ctypes.data,
+                              memspace=_native.B2_DEVICE)
+
+
+# ======================================================= BASELINE configs[2] at its stated size
+
+def test_sync_batch_config3_256_pairs_vs_oracle(handle):
+    """B = 256 two-hour pairs, K = 5 (the benchmarked configuration: n_split = 1, 1280 correlation
+    jobs, winner-only pruning): every ratio of a seeded sample of 8 pairs against the oracle (offset
+    exact, score <= 1e-5), winner triples of the all-ratio and the winner-only runs identical, and
+    the planted (offset, ratio) recovered on all 256 pairs."""
+    import torch
+    import bench
+    from ffsubsync_b200 import _native
+    from ffsubsync_b200.batch import BatchSynchronizer
+    from ffsubsync_b200.synth import BENCH_RATIOS, make_pairs
+    B, ratios = 256, BENCH_RATIOS
+    bs = BatchSynchronizer(ratios, 16000, 100, 0.0, max_offset_seconds=60)
+    pairs = make_pairs([13 + b for b in range(B)], 7200.0, ratios, handle=bs.handle)
+    n_win = int(pairs.win_off[-1])
+    cls_d = torch.from_numpy(pairs.window_class).cuda()
+    pcm_d = torch.empty(n_win * 160, dtype=torch.int16, device="cuda")
+    bs.handle.synth_pcm(cls_d.data_ptr(), n_win, 160, 1234, out=pcm_d.data_ptr(), memspace=_native.B2_DEVICE)
+    bs.handle.synchronize()
+    del cls_d
+    pcm_off = pairs.win_off * 160
+    rep = bench.verify_against_oracle(bs, pairs, pcm_d, pcm_off, ratios, 8, 2024 + B)
+    assert rep["ok"], rep
+    assert rep["winner_only_equals_all_ratios"] and len(rep["pairs_checked"]) == 8
+    out = bs.sync_device(pcm_d, pcm_off, pairs.cue_start, pairs.cue_end, pairs.cue_off)
+    torch.cuda.synchronize()
+    assert (out["best_offset"].cpu().numpy() == pairs.true_offset).all()
+    assert (out["best_k"].cpu().numpy() == pairs.true_k).all()
+    del pcm_d
+    torch.cuda.empty_cache()

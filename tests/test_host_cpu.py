@@ -36,7 +36,7 @@ def test_library_exports_every_header_symbol(built):
     lib = ctypes.CDLL(_native.LIB_PATH)
     for name in declared:
         assert hasattr(lib, name), name
-    assert _native.load().b2_version() == 100
+    assert _native.load().b2_version() == 200
     # every declaration cites the reference interface it replaces
     assert header.count("ffsubsync/") >= 8
 
@@ -278,3 +278,37 @@ def test_raw_pcm_window_follows_ss_t():
     stream, total, _ = v._open_source((np.arange(16000 * 10) % 30000).astype(np.int16))
     data = np.frombuffer(stream.read(1 << 30), np.int16)
     assert total == 2.0 and len(data) == 32000 and data[0] == 18000
+
+
+def test_auditok_host_helpers_match_the_oracle():
+    """b2_auditok_block_size / b2_auditok_energy_floor are host-only entry points (no GPU): the
+    integer energy floor the kernel compares against equals the one found by evaluating the
+    validator's float64 expression in numpy (oracle/auditok_oracle.py)."""
+    from ffsubsync_b200 import _native
+    from oracle import auditok_oracle as au
+    lib = _native.load()
+    for fr, sr in ((16000, 100), (48000, 100), (44100, 100), (8000, 100), (22050, 100), (11025, 100)):
+        assert lib.b2_auditok_block_size(fr, sr) == fr // sr == int(fr * (1.0 / sr))
+    assert lib.b2_auditok_block_size(49, 49) == 0   # int(49 * (1/49)) = 0 != 49 // 49: unsupported
+    for n in (1, 2, 7, 80, 159, 160, 220, 441, 480, 1000):
+        for thr in (50, 50.0, 45, 30.5, 0, 62.25, 90.3):
+            assert lib.b2_auditok_energy_floor(n, float(thr)) == au.energy_floor(n, thr), (n, thr)
+    assert lib.b2_auditok_energy_floor(160, -250.0) == 0           # even silence (-200) passes
+    assert lib.b2_auditok_energy_floor(160, 200.0) == 2 ** 63 - 1   # unreachable for int16 blocks
+
+
+def test_mask_width_marshalling():
+    from ffsubsync_b200 import _native
+    assert _native._mask_width(None) == -(1 << 63) == _native.B2_MAX_OFFSET_NONE
+    assert _native._mask_width(-1) == -1 and _native._mask_width(6000) == 6000
+    assert _native._mask_width(1 << 80) == 1 << 62 and _native._mask_width(-(1 << 80)) == -(1 << 62)
+
+
+def test_pipeline_maker_keeps_the_reference_signature():
+    import inspect
+    from ffsubsync_b200.speech_transformers import make_subtitle_speech_pipeline
+    names = list(inspect.signature(make_subtitle_speech_pipeline).parameters)
+    assert names[:7] == ["fmt", "encoding", "caching", "max_subtitle_seconds", "start_seconds", "scale_factor",
+                         "parser"]
+    with pytest.raises(ValueError):
+        make_subtitle_speech_pipeline("srt")   # a caller written for the reference: no silent mis-binding

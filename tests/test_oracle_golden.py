@@ -227,3 +227,91 @@ def test_vad_contract_and_synthetic_classes():
     assert np.array_equal(np.concatenate([a, b]), out)
     e, z = vo.window_features(pcm, fpw)
     assert z[1] == 3 and e[1] > fpw * 10**5 and e[0] < fpw * 10**5 and z[2] > 60
+
+
+# ===================================================================== auditok detector (V3) pins
+# The auditok wheel is absent: the restatement in oracle/auditok_oracle.py is pinned to the
+# known-answer examples of auditok 0.1.5's StreamTokenizer documentation / test-suite (quoted from
+# memory, see the oracle header) and to the arithmetic identity of its energy rule.
+
+def _upper(s):
+    return [c.isupper() for c in s]
+
+
+@pytest.mark.parametrize("text, min_len, max_len, max_sil, want", [
+    ("aaaAAAABBbbb", 1, 9999, 0, [(3, 8)]),
+    ("aaaAAAABBbbb", 3, 4, 0, [(3, 6), (7, 8)]),                 # short token kept: contiguous with a truncated one
+    ("aaaAAAaaaBBbbbb", 3, 6, 3, [(3, 8), (9, 13)]),            # trailing silence is part of the token
+    ("aAaaaAaAaaAaAaaaaaaaAAAAAAAA", 5, 20, 4, [(1, 16), (20, 27)]),
+])
+def test_auditok_tokenizer_published_examples(text, min_len, max_len, max_sil, want):
+    from oracle import auditok_oracle as au
+    assert au.tokenize(_upper(text), min_len, max_len, max_sil) == want
+
+
+def test_auditok_energy_rule_is_an_integer_threshold():
+    """10*log10(dot(x,x)/n) >= 50  <=>  sum x^2 >= n * 10^5 for int16 blocks, exact-edge blocks included."""
+    from oracle import auditok_oracle as au
+    rng = np.random.RandomState(3)
+    for n in (1, 7, 80, 159, 160, 441, 480):
+        assert au.energy_floor(n, 50) == n * 10 ** 5
+        for _ in range(60):   # rms around the 50 dB edge (sqrt(1e5) = 316.2)
+            x = np.round(rng.randn(n) * rng.uniform(250, 400)).astype(np.int16)
+            e = int((x.astype(np.int64) ** 2).sum())
+            assert au.block_is_valid(x, 50) == (e >= n * 10 ** 5)
+    # exact edge: 100 samples of +-400 and 60 zeros give 16 000 000 = 160 * 10^5; one LSB less is invalid
+    x = np.zeros(160, np.int16)
+    x[:100] = 400
+    assert au.block_is_valid(x, 50) and au.block_log_energy(x) == 50.0
+    x[0] = 399
+    assert not au.block_is_valid(x, 50)
+    assert not au.block_is_valid(np.zeros(160, np.int16), 50)   # log energy -200
+
+
+def test_auditok_detect_wrapper_semantics():
+    """speech_transformers.py:143-150: length formula, impulse ASSIGNMENT and the cumsum/clip."""
+    from oracle import auditok_oracle as au
+    fpw = 160
+    loud = (np.tile([400, -400], fpw // 2)).astype(np.int16)       # E = 160 * 160000 >= 160 * 1e5
+    quiet = np.zeros(fpw, np.int16)
+
+    def build(flags, tail=0):
+        pcm = np.concatenate([loud if f else quiet for f in flags] + [loud[:tail]])
+        return pcm.tobytes()
+
+    # 30 valid blocks, 40 silent: token = 30 + 25 tolerated silent frames
+    out = au.auditok_detect(build([1] * 30 + [0] * 40), 100, 16000, 0.0)
+    assert len(out) == 70 and out[:55].tolist() == [1.0] * 55 and out[55:].tolist() == [0.0] * 15
+    # a 10-frame blip is shorter than min_length = 20 (even with its tolerated silence it is judged on
+    # len(data) = 10 + 25): 35 >= 20 -> delivered; a blip with the stream ending right after is not
+    out = au.auditok_detect(build([0] * 5 + [1] * 10 + [0] * 50), 100, 16000, 0.0)
+    assert out[5:40].tolist() == [1.0] * 35 and out[40:].sum() == 0
+    out = au.auditok_detect(build([0] * 5 + [1] * 10), 100, 16000, 0.0)
+    assert out.sum() == 0   # post-processing: 10 < min_length and not contiguous
+    # 600 valid blocks: truncated at max_length = 500; the next token starts where the end impulse of
+    # the first one was written and OVERWRITES it, so the level stays at 1 after the second token ends
+    out = au.auditok_detect(build([1] * 600 + [0] * 100), 100, 16000, 0.0)
+    assert len(out) == 700 and out.tolist() == [1.0] * 700
+    out = au.auditok_detect(build([1] * 600 + [0] * 100), 100, 16000, 0.25)   # cumsum 1, 2, 1.25 -> clip
+    assert out[:625].tolist() == [1.0] * 625 and out[625:].tolist() == [1.0] * 75
+    # partial last block: judged on the samples it has; output length = ceil(n / fpw)
+    out = au.auditok_detect(build([1] * 40, tail=7), 100, 16000, 0.0)
+    assert len(out) == 41 and out.tolist() == [1.0] * 41
+    with pytest.raises(ValueError):
+        au.auditok_detect(b"\x00\x01\x02", 100, 16000, 0.0)
+
+
+def test_auditok_fast_path_equals_literal_restatement():
+    from oracle import auditok_oracle as au
+    rng = np.random.RandomState(8)
+    for frame_rate, nsl in ((16000, 0.0), (8000, 0.3), (44100, 0.0)):
+        fpw = frame_rate // 100
+        runs, valid = [], True
+        while sum(runs) < 4000:
+            runs.append(int(rng.choice([2, 8, 19, 20, 24, 25, 26, 60, 300, 520])))
+        amp = np.concatenate([np.full(r, 1.15 if (i % 2 == 0) else 0.85) for i, r in enumerate(runs)])
+        amp = amp * rng.uniform(0.93, 1.07, len(amp))
+        pcm = np.round(rng.randn(len(amp) * fpw) * 316.2 * np.repeat(amp, fpw)).astype(np.int16)[: len(amp) * fpw - 13]
+        a = au.auditok_detect(pcm.tobytes(), 100, frame_rate, nsl)
+        b = au.auditok_detect_fast(pcm.tobytes(), 100, frame_rate, nsl)
+        assert np.array_equal(a, b) and 0 < a.sum() < len(a)
