@@ -107,6 +107,60 @@ class BatchSynchronizer:
         h.synchronize()
         return bs.cpu().numpy(), bo.cpu().numpy(), bk.cpu().numpy()
 
+    def sync_device_candidate_sharded(self, pcm, pcm_off, cue_start, cue_end, cue_off, cue_keep=None,
+                                      rank: int = 0, world: int = 1, group=None):
+        """Secondary multi-GPU mode ("B < G": a few pairs on many GPUs): the K
+        ratio candidates of every pair are dealt round-robin over the ranks.  Every rank runs the
+        VAD of the (replicated) reference PCM - 33 us per 2 h signal, cheaper than shipping the
+        signal - rasterises and aligns only ITS candidates (b2_align_batch with K_local ratios),
+        the per-candidate (score, offset, status) triples are all-gathered back into list order
+        (NCCL, 24 B per candidate) and b2_reduce_ratios applies the |offset| filter and the
+        first-in-list tie rule on every rank, so all ranks hold the same (score, offset, ratio index)
+        as a single-GPU run.  pcm: int16 CUDA tensor, same on every rank.  Returns CUDA tensors
+        (best_score f64[B], best_offset i32[B], best_k i32[B])."""
+        import torch
+        from . import distributed
+        h = self.handle
+        self.use_torch_stream()   # torch ops and NCCL below are ordered against our kernels by the stream
+        pcm_off = np.ascontiguousarray(pcm_off, dtype=np.int64)
+        B, K = len(pcm_off) - 1, len(self.ratios)
+        dev = pcm.device
+        mine = distributed.shard_candidates(K, rank, world)
+        fpw = h.frames_per_window(self.frame_rate, self.sample_rate)
+        ref_off = np.concatenate([[0], np.cumsum((np.diff(pcm_off) + fpw - 1) // fpw)]).astype(np.int64)
+        ref = torch.empty(int(ref_off[-1]), dtype=torch.float32, device=dev)
+        h.vad_energy_zcr(pcm.data_ptr(), pcm_off, self.frame_rate, self.sample_rate, self.non_speech_label,
+                         self.energy_threshold, self.z_lo, self.z_hi, out=ref.data_ptr(), memspace=_native.B2_DEVICE)
+        k_loc = len(mine)
+        local = torch.zeros((B, max(k_loc, 1), 3), dtype=torch.float64, device=dev)
+        if k_loc:
+            my_ratios = self.ratios[mine]
+            lengths = h.rasterize_lengths(cue_end, cue_off, my_ratios, k_loc, False, self.sample_rate)
+            sub_off = np.concatenate([[0], np.cumsum(lengths)]).astype(np.int64)
+            sub = torch.empty(int(sub_off[-1]), dtype=torch.float32, device=dev)
+            h.rasterize(cue_start, cue_end, cue_keep, cue_off, my_ratios, k_loc, False, self.sample_rate,
+                        self.start_seconds, out=sub.data_ptr(), out_off=sub_off, memspace=_native.B2_DEVICE)
+            score = torch.empty(B * k_loc, dtype=torch.float64, device=dev)
+            offset = torch.empty(B * k_loc, dtype=torch.int32, device=dev)
+            status = torch.empty(B * k_loc, dtype=torch.int32, device=dev)
+            h.align_batch(ref.data_ptr(), ref_off, sub.data_ptr(), sub_off, B, k_loc, self.max_offset_samples,
+                          score=score.data_ptr(), offset=offset.data_ptr(), status=status.data_ptr(),
+                          memspace=_native.B2_DEVICE)
+            local[:, :, 0] = score.view(B, k_loc)
+            local[:, :, 1] = offset.view(B, k_loc).to(torch.float64)
+            local[:, :, 2] = status.view(B, k_loc).to(torch.float64)
+        full = distributed.allgather_candidate_results(local[:, :k_loc], K, rank, world, group=group)
+        score_all = full[:, :, 0].contiguous().view(-1)
+        offset_all = full[:, :, 1].to(torch.int32).contiguous().view(-1)
+        status_all = full[:, :, 2].to(torch.int32).contiguous().view(-1)
+        bs = torch.empty(B, dtype=torch.float64, device=dev)
+        bo = torch.empty(B, dtype=torch.int32, device=dev)
+        bk = torch.empty(B, dtype=torch.int32, device=dev)
+        h.reduce_ratios(score_all.data_ptr(), offset_all.data_ptr(), status_all.data_ptr(), B, K,
+                        self.max_offset_samples, best_score=bs.data_ptr(), best_offset=bo.data_ptr(),
+                        best_k=bk.data_ptr(), memspace=_native.B2_DEVICE)
+        return bs, bo, bk
+
     def sync_host(self, pcm, pcm_off, cue_start, cue_end, cue_off, cue_keep=None, want_all=False):
         """pcm: int16 numpy array (ideally backed by pinned memory).  Blocks until results are on
         the host.  Returns (best_score, best_offset, best_k[, all_score, all_offset])."""

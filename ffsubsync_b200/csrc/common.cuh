@@ -41,6 +41,8 @@ struct b2_ctx {
   uint64_t log2_quirk_mask = 0;  // bit k set: CPython's ceil(math.log(2**k, 2)) == k + 1
   int acc_in_tmem = 1;           // correlation accumulators in tensor memory (B2_ACC=reg: registers)
   int vad_ctas_per_sm = 0;       // 0 = as many as fit; set to 1 while b2_sync_batch pipelines
+  int vad_partition_sms = 0;     // > 0: the VAD launches 512-consumer CTAs, one per SM, on this many SMs
+  int corr_max_ctas = 0;         // > 0: persistent correlation kernels use at most this many CTAs
   // named grow-only workspaces
   enum { WS_STAGE_IN0, WS_STAGE_IN1, WS_STAGE_OUT, WS_META, WS_SPEC, WS_SCORES, WS_CAND,
          WS_SIG_REF, WS_SIG_SUB, WS_MISC, WS_COUNTERS, WS_COUNT };

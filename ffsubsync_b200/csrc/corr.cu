@@ -13,8 +13,8 @@
 // a P = 2^15 point real FFT that lives entirely in shared memory, conj(A)*B is accumulated over
 // the blocks in registers, and ONE inverse transform yields the W scores (overlap-save
 // correlation).  The reference-side spectra are computed once per pair and reused by all K
-// ratio candidates.  The fp32 scores only nominate candidates: every offset within a proven
-// round-off bound of the maximum is re-scored exactly (float64 direct sum), so the returned
+// ratio candidates.  The fp32 scores only nominate candidates: every offset within a first-order
+// worst-case round-off bound (tau, below) of the maximum is re-scored exactly (float64 direct sum), so the returned
 // offset and score do not depend on FFT round-off.  Offset ranges wider than P/2 are tiled.
 #include <math.h>
 
@@ -29,9 +29,27 @@ using namespace corr;
 
 constexpr int kCandMax = 32;
 constexpr int kRescoreSeg = 16;
-// candidates within kTauRel * sqrt(Es*Er) of the fp32 maximum are re-scored exactly; measured
-// round-off of the chain is < 6 * 2^-24 * sqrt(Es*Er) (tests/test_corr_emul.py, tests/test_gpu_align.py)
-constexpr float kTauRel = 64.0f * 5.9604645e-8f;
+// Nomination threshold tau ("Round-off bound"): every offset whose fp32 score
+// is within tau of the fp32 maximum is re-scored exactly, with
+//     tau = u * (kTauFwd * sqrt(Es*Er) + (kTauInv + n_split - 1) * ||c||_2),   u = 2^-24,
+// a first-order WORST-CASE bound on |fp32 score - exact score| (all rounding errors aligned):
+//   kTauFwd: both forward transforms (first pass 95u: the twiddle w^k of the depth-4 product chain
+//            carries k <= 15 times the 5.7u error of the two-table base twiddle; passes 2-4
+//            32u + 22u + 3u; untangle 16u) = 2 x 168u, spectral product 3u, accumulation over
+//            <= 64 blocks in fp32 <= 63u (more blocks: see window_max_kernel), retangle 16u -> <= 418u,
+//            rounded up to 512 for the second-order terms;
+//   kTauInv: the inverse transform is backward stable in the 2-norm, |error[m]| <= eps_inv*||c||_2
+//            with eps_inv = 16u + 3u + 22u + 32u + 95u = 168u -> 192; ||c||_2 is the norm of the
+//            tile's whole inverse-transform output, computed by the kernel (it exceeds sqrt(Es*Er)
+//            only for signals with a large mean, whose correlation is a broad ramp);
+//   n_split - 1: fp32 addition of the partial score arrays of a split job.
+// Measured on random, constant, periodic, sparse and wide-dynamic-range inputs the error stays
+// below 12 u sqrt(Es*Er) (tests/test_host_cpu.py::test_roundoff_bound_*): the bound has > 40x slack,
+// and costs nothing on real data, where the runner-up is thousands of units below the peak.
+constexpr float kU = 5.9604645e-8f;
+constexpr float kTauFwd = 512.0f;
+constexpr float kTauInv = 192.0f;
+constexpr int kTauBlocks = 64;  // block count covered by kTauFwd
 
 struct SpecItem {      // one reference block to transform
   long long ref_off;   // element offset of the pair's reference signal
@@ -227,7 +245,7 @@ template <bool TMEM, bool BITS, int DEPTH = 2>
 __device__ __forceinline__ void sub_correlate_body(
     const float* __restrict__ sub, const SubJob* __restrict__ jobs, const float4* __restrict__ spec,
     const float* __restrict__ spec_energy, int L, float* __restrict__ scores,
-    float2* __restrict__ job_energy, const uint32_t* __restrict__ sub_bits) {
+    float4* __restrict__ job_energy, const uint32_t* __restrict__ sub_bits) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   float2* buf = reinterpret_cast<float2*>(smem_raw);
   float2* tw1024 = buf + kM;
@@ -240,7 +258,7 @@ __device__ __forceinline__ void sub_correlate_body(
   float* out = scores + job.score_off;
   if (job.blk_lo >= job.blk_hi) {  // no subtitle block meets the reference at these offsets
     for (int m = tid; m < job.n_out; m += kThreads) out[m] = 0.f;
-    if (tid == 0) job_energy[job.energy_slot] = make_float2(0.f, 0.f);
+    if (tid == 0) job_energy[job.energy_slot] = make_float4(0.f, 0.f, 0.f, 0.f);
     return;
   }
   init_tables(tw1024, fine32, tid);
@@ -329,14 +347,32 @@ __device__ __forceinline__ void sub_correlate_body(
   inverse_passes_4(buf, t, tid);
   __syncthreads();
   for (int m = tid; m < job.n_out; m += kThreads) out[m] = window_value(buf, m);
+  // ||c||_2^2 of the whole inverse-transform output (all kP real values, in score units): the
+  // quantity the inverse transform's round-off is relative to (tau, window_max_kernel)
+  float cn = 0.f;
+  for (int i = tid; i < kM; i += kThreads) {
+    const float2 z = buf[i];
+    cn = fmaf(z.x, z.x, fmaf(z.y, z.y, cn));
+  }
+  cn *= kOutScale * kOutScale;
   float ss = st.ss;
-  for (int o = 16; o > 0; o >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o);
-  if ((tid & 31) == 0) red[tid >> 5] = ss;
+  for (int o = 16; o > 0; o >>= 1) {
+    ss += __shfl_xor_sync(0xffffffffu, ss, o);
+    cn += __shfl_xor_sync(0xffffffffu, cn, o);
+  }
+  __shared__ float red2[kThreads / 32];
+  if ((tid & 31) == 0) {
+    red[tid >> 5] = ss;
+    red2[tid >> 5] = cn;
+  }
   __syncthreads();
   if (tid == 0) {
-    float e = 0.f;
-    for (int w = 0; w < kThreads / 32; ++w) e += red[w];
-    job_energy[job.energy_slot] = make_float2(e, er);
+    float e = 0.f, c2 = 0.f;
+    for (int w = 0; w < kThreads / 32; ++w) {
+      e += red[w];
+      c2 += red2[w];
+    }
+    job_energy[job.energy_slot] = make_float4(e, er, c2, (float)(job.blk_hi - job.blk_lo));
   }
   if (TMEM) {
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -354,7 +390,7 @@ constexpr int kSubRegs = 96;
 __global__ void __maxnreg__(kSubRegs)
     sub_correlate_kernel(const float* __restrict__ sub, const SubJob* __restrict__ jobs,
                          const float4* __restrict__ spec, const float* __restrict__ spec_energy,
-                         int L, float* __restrict__ scores, float2* __restrict__ job_energy) {
+                         int L, float* __restrict__ scores, float4* __restrict__ job_energy) {
   sub_correlate_body<true, false>(sub, jobs, spec, spec_energy, L, scores, job_energy, nullptr);
 }
 
@@ -362,7 +398,7 @@ __global__ void __maxnreg__(kSubRegs)
 __global__ void __maxnreg__(kSubRegs)
     sub_correlate_bits_kernel(const SubJob* __restrict__ jobs, const float4* __restrict__ spec,
                               const float* __restrict__ spec_energy, int L,
-                              float* __restrict__ scores, float2* __restrict__ job_energy,
+                              float* __restrict__ scores, float4* __restrict__ job_energy,
                               const uint32_t* __restrict__ sub_bits) {
   sub_correlate_body<true, true>(nullptr, jobs, spec, spec_energy, L, scores, job_energy, sub_bits);
 }
@@ -372,8 +408,18 @@ __global__ void __launch_bounds__(kThreads, 1)
     sub_correlate_regacc_kernel(const float* __restrict__ sub, const SubJob* __restrict__ jobs,
                                 const float4* __restrict__ spec,
                                 const float* __restrict__ spec_energy, int L,
-                                float* __restrict__ scores, float2* __restrict__ job_energy) {
+                                float* __restrict__ scores, float4* __restrict__ job_energy) {
   sub_correlate_body<false, false>(sub, jobs, spec, spec_energy, L, scores, job_energy, nullptr);
+}
+
+// Same for the bit-mask path (compute-sanitizer's synccheck does not model tcgen05.alloc; the
+// sanitizer runs use B2_ACC=reg).
+__global__ void __launch_bounds__(kThreads, 1)
+    sub_correlate_bits_regacc_kernel(const SubJob* __restrict__ jobs, const float4* __restrict__ spec,
+                                     const float* __restrict__ spec_energy, int L,
+                                     float* __restrict__ scores, float4* __restrict__ job_energy,
+                                     const uint32_t* __restrict__ sub_bits) {
+  sub_correlate_body<false, true>(nullptr, jobs, spec, spec_energy, L, scores, job_energy, sub_bits);
 }
 
 // ---- candidate selection ---------------------------------------------------------------------
@@ -383,7 +429,7 @@ __global__ void __launch_bounds__(kThreads, 1)
 // Phase 1: fp32 maximum of the surviving window and the round-off bound tau, per (pair, ratio).
 __global__ void __launch_bounds__(256) window_max_kernel(const SelJob* __restrict__ jobs,
                                                           float* __restrict__ scores,
-                                                          const float2* __restrict__ job_energy,
+                                                          const float4* __restrict__ job_energy,
                                                           float2* __restrict__ job_stat, int wt) {
   const SelJob job = jobs[blockIdx.x];
   const int tid = threadIdx.x;
@@ -411,17 +457,23 @@ __global__ void __launch_bounds__(256) window_max_kernel(const SelJob* __restric
     __syncthreads();
   }
   if (tid == 0) {
-    float e2 = 0.f;
+    float tau = 0.f;
     for (int i = 0; i < job.n_tiles; ++i) {
-      float ex = 0.f, ey = 0.f;  // energies add over the chunks of a tile (Cauchy-Schwarz bound)
+      // energies add over the chunks of a tile (Cauchy-Schwarz); the norms of the partial inverse
+      // transforms add (triangle inequality); blocks beyond kTauBlocks add u each to the
+      // accumulation term
+      float ex = 0.f, ey = 0.f, cn = 0.f, blocks = 0.f;
       for (int sp = 0; sp < job.n_split; ++sp) {
-        const float2 e = job_energy[job.energy_slot + i * job.n_split + sp];
+        const float4 e = job_energy[job.energy_slot + i * job.n_split + sp];
         ex += e.x;
         ey += e.y;
+        cn += sqrtf(e.z);
+        blocks = fmaxf(blocks, e.w);
       }
-      e2 = fmaxf(e2, ex * ey);
+      const float fwd = kTauFwd + fmaxf(0.f, blocks - (float)kTauBlocks);
+      tau = fmaxf(tau, kU * (fwd * sqrtf(ex * ey) + (kTauInv + (float)(job.n_split - 1)) * cn));
     }
-    job_stat[blockIdx.x] = make_float2(smax[0], kTauRel * sqrtf(e2) + 1e-30f);
+    job_stat[blockIdx.x] = make_float2(smax[0], tau * 1.0001f + 1e-30f);
   }
 }
 
@@ -717,6 +769,8 @@ int b2i_align_launch(b2_ctx* h, const float* d_ref, const int64_t* ref_off, cons
     B2_TRY(b2i_raster_bits_launch(h, cue_src, B, K, sub_off, bits_off.data(), d_bits));
     B2_CUDA(h, cudaFuncSetAttribute(sub_correlate_bits_kernel,
                                     cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytesBits));
+    B2_CUDA(h, cudaFuncSetAttribute(sub_correlate_bits_regacc_kernel,
+                                    cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytesBits));
   }
 
   // score buffers + per-(pair,ratio) bookkeeping
@@ -760,10 +814,10 @@ int b2i_align_launch(b2_ctx* h, const float* d_ref, const int64_t* ref_off, cons
   }
 
   void *d_scores, *d_cand;
-  B2_TRY(b2i_ws(h, b2_ctx::WS_SCORES, (size_t)(score_total + 16) * 4 + (size_t)(energy_total + 1) * 8,
+  B2_TRY(b2i_ws(h, b2_ctx::WS_SCORES, (size_t)(score_total + 16) * 4 + (size_t)(energy_total + 2) * 16,
                 &d_scores));
   float* scores = (float*)d_scores;
-  float2* job_energy = (float2*)((char*)d_scores + (((size_t)(score_total + 16) * 4 + 7) & ~size_t(7)));
+  float4* job_energy = (float4*)((char*)d_scores + (((size_t)(score_total + 16) * 4 + 15) & ~size_t(15)));
   B2_TRY(b2i_ws(h, b2_ctx::WS_CAND, J * kCandMax * (8 * kRescoreSeg + 8) + J * 12 + 64, &d_cand));
   double* cand_partial = (double*)d_cand;
   float2* job_stat = (float2*)(cand_partial + J * kCandMax * kRescoreSeg);
@@ -799,13 +853,19 @@ int b2i_align_launch(b2_ctx* h, const float* d_ref, const int64_t* ref_off, cons
     const SubJob* d_jobs = (const SubJob*)b2i_meta_put(&a, jobs.data(), jobs.size() * sizeof(SubJob));
     B2_TRY(b2i_meta_commit(&a));
     if (!items.empty()) {
-      const unsigned grid = (unsigned)std::min<size_t>(items.size(), (size_t)h->sm_count);
+      // persistent: one CTA per SM - or per SM the pipeline leaves to the correlation stage
+      int max_ctas = h->corr_max_ctas > 0 ? std::min(h->corr_max_ctas, h->sm_count) : h->sm_count;
+      if (const char* e = getenv("B2_CORR_MAX_CTAS")) max_ctas = std::max(1, std::min(h->sm_count, atoi(e)));  // probe knob
+      const unsigned grid = (unsigned)std::min<size_t>(items.size(), (size_t)max_ctas);
       ref_spectra_kernel<<<grid, kThreads, kSmemBytes, h->stream>>>(d_ref, d_items, (int)items.size(),
                                                                     spec, spec_energy);
       B2_CHECK_LAUNCH(h, "ref_spectra_kernel");
     }
-    if (cue_mode)
+    if (cue_mode && h->acc_in_tmem)
       sub_correlate_bits_kernel<<<(unsigned)jobs.size(), kThreads, kSmemBytesBits, h->stream>>>(
+          d_jobs, spec, spec_energy, L, scores, job_energy, d_bits);
+    else if (cue_mode)
+      sub_correlate_bits_regacc_kernel<<<(unsigned)jobs.size(), kThreads, kSmemBytesBits, h->stream>>>(
           d_jobs, spec, spec_energy, L, scores, job_energy, d_bits);
     else if (h->acc_in_tmem)
       sub_correlate_kernel<<<(unsigned)jobs.size(), kThreads, kSmemBytes, h->stream>>>(

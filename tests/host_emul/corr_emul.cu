@@ -7,7 +7,8 @@
 // in.bin : int32 R, S, o_t, W, L, mode ; float ref[R] ; float sub[S]
 //          mode 0: float subtitle signal (sub_correlate_kernel);  mode 1: two-level subtitle signal
 //          {0, level} fed as a bit mask (sub_correlate_bits_kernel; L must be a multiple of 32)
-// out.bin: float c[W]  (c[m] ~ sum_j sub'[j] ref'[j + o_t + m]) ; float Es, Er
+// out.bin: float c[W]  (c[m] ~ sum_j sub'[j] ref'[j + o_t + m]) ; float Es, Er, ||c||_2^2 of the whole
+//          inverse-transform output (what sub_correlate_body stores for tau), blocks accumulated
 #include <stdio.h>
 #include <stdlib.h>
 #include <vector>
@@ -47,9 +48,11 @@ int main(int argc, char** argv) {
   std::vector<uint32_t> words(kP / 32);
 
   const int nblk = (S + L - 1) / L;
+  int n_acc = 0;
   for (int blk = 0; blk < nblk; ++blk) {
     const int j0 = blk * L, i0 = j0 + o_t;
     if (i0 >= R || i0 + kP <= 0) continue;  // block pruning, as the host planner does
+    ++n_acc;
     // reference block (ref_spectra_kernel)
     const int r_lo = i0 < 0 ? -i0 : 0, r_hi = (R - i0) < kP ? (R - i0) : kP;
     for (int tid = 0; tid < kThreads; ++tid)
@@ -82,14 +85,17 @@ int main(int argc, char** argv) {
   for (int tid = 0; tid < kThreads; ++tid) inverse_passes_2(buf.data(), t, tid);
   for (int tid = 0; tid < kThreads; ++tid) inverse_passes_3(buf.data(), t, tid);
   for (int tid = 0; tid < kThreads; ++tid) inverse_passes_4(buf.data(), t, tid);
-  std::vector<float> out(W + 2);
+  std::vector<float> out(W + 4);
   for (int m = 0; m < W; ++m) out[m] = window_value(buf.data(), m);
-  float es = 0.f, er = 0.f;
+  float es = 0.f, er = 0.f, cn = 0.f;
   for (int tid = 0; tid < kThreads; ++tid) { es += ss_sub[tid]; er += ss_ref[tid]; }
+  for (int i = 0; i < kM; ++i) cn += buf[i].x * buf[i].x + buf[i].y * buf[i].y;
   out[W] = es;
   out[W + 1] = er;
+  out[W + 2] = cn * kOutScale * kOutScale;
+  out[W + 3] = (float)n_acc;
   f = fopen(argv[2], "wb");
-  fwrite(out.data(), 4, W + 2, f);
+  fwrite(out.data(), 4, W + 4, f);
   fclose(f);
   return 0;
 }

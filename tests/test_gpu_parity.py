@@ -767,7 +767,7 @@ def test_auditok_detector_matches_oracle(handle, frame_rate, label):
         got = det(np.frombuffer(pcm.tobytes(), np.uint8))
         assert got.dtype == np.float64 and len(got) == len(want)
         assert np.array_equal(got, want), (frame_rate, label, n_blocks, cut, int(np.argmax(got != want)))
-        assert 0 < want.sum()
+        assert n_blocks < 600 or 0 < want.sum() < len(want) or label > 0
     assert len(det(b"")) == 0
     with pytest.raises(ValueError):
         det(b"\x01\x02\x03")
@@ -893,3 +893,29 @@ def test_sync_batch_config3_256_pairs_vs_oracle(handle):
     assert (out["best_k"].cpu().numpy() == pairs.true_k).all()
     del pcm_d
     torch.cuda.empty_cache()
+
+
+def test_candidate_sharded_mode_single_rank_equals_sync_batch(handle):
+    """The B < G mode's compute path (VAD -> own candidates -> reduce) with world = 1 equals
+    b2_sync_batch; the multi-rank exchange is covered by the gloo test and tools/candidate_mode_bench.py."""
+    import torch
+    from ffsubsync_b200 import _native
+    from ffsubsync_b200.batch import BatchSynchronizer
+    from ffsubsync_b200.constants import FRAMERATE_RATIOS
+    from ffsubsync_b200.synth import make_pairs
+    r = np.array(FRAMERATE_RATIOS)
+    ratios = [1.0] + list(np.concatenate([r, 1.0 / r]))
+    bs = BatchSynchronizer(ratios, 16000, 100, 0.0, max_offset_seconds=60)
+    pairs = make_pairs([5, 6, 7], 600.0, ratios, handle=bs.handle)
+    n_win = int(pairs.win_off[-1])
+    cls_d = torch.from_numpy(pairs.window_class).cuda()
+    pcm = torch.empty(n_win * 160, dtype=torch.int16, device="cuda")
+    bs.handle.synth_pcm(cls_d.data_ptr(), n_win, 160, 9, out=pcm.data_ptr(), memspace=_native.B2_DEVICE)
+    bs.handle.synchronize()
+    args = (pcm, pairs.win_off * 160, pairs.cue_start, pairs.cue_end, pairs.cue_off)
+    a = bs.sync_device_candidate_sharded(*args)
+    b = bs.sync_device(*args)
+    bs.handle.synchronize()
+    torch.cuda.synchronize()
+    assert torch.equal(a[1], b["best_offset"]) and torch.equal(a[2], b["best_k"]) and torch.equal(a[0], b["best_score"])
+    assert (a[1].cpu().numpy() == pairs.true_offset).all() and (a[2].cpu().numpy() == pairs.true_k).all()
