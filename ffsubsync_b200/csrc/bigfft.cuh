@@ -1,0 +1,490 @@
+// Device building blocks of the LARGE-WINDOW correlation (FFTAligner with max_offset_samples=None
+// or a mask wider than a few overlap-save tiles; ffsubsync/aligners.py:67-80): one real FFT of the
+// padded length N = 2 M per signal, done as a four-step complex FFT of M = M1 x 1024 points over
+// HBM / L2, every step a batched in-shared-memory transform of one 16 384-point tile:
+//
+//   F1  columns: tile = all M1 rows x (16384 / M1) adjacent columns, row-major exactly as in global
+//       memory (coalesced, no transpose): the column FFT over n1 is the TOP log2(M1) levels of the
+//       16 384-point decimation-in-frequency network (passes at strides 1024, 64 and "cols", twiddles
+//       taken at the column-cleared index), then the four-step twiddle w_M^(n2 k1), stored k1-major.
+//   F2  rows:    tile = 8 rows + their 8 partner rows (k1 <-> M1 - k1), each a contiguous 1024-point
+//       transform (the passes corr.cuh already has); the real-FFT untangle pairs element (k1, k2)
+//       with (M1 - k1, 1023 - k2) = the mirrored POSITION in the partner row.  Reference: store the
+//       spectrum.  Subtitles: conj(A) * B, retangle, inverse row transform and the conjugate
+//       four-step twiddle in the same kernel (one global round trip saved).
+//   F3  columns, inverse: the mirror of F1; writes the N scores, their maximum over the surviving
+//       window and the sum of squares (the norm the round-off bound needs).
+//
+// Like corr.cuh everything is __host__ __device__: tests/host_emul/bigfft_emul.cu runs the same
+// code thread by thread on the CPU against np.fft (the build container has no GPU).
+#pragma once
+#include "corr.cuh"
+
+namespace bigfft {
+
+using namespace corr;
+
+constexpr int kRow = 1024;      // M2: row length of the four-step factorisation
+constexpr int kMinQ1 = 6;       // M1 = 2^q1 rows, 64 ... 4096  ->  N = 2^17 ... 2^23
+constexpr int kMaxQ1 = 12;
+
+// ---- small DFTs without twiddles ---------------------------------------------------------------
+template <bool INV>
+CORR_HD void r2(float2& a0, float2& a1) {
+  const float2 s = cadd(a0, a1), d = csub(a0, a1);
+  a0 = s;
+  a1 = d;
+}
+
+// multiply by exp(-+ 2 pi i n / 8)
+template <bool INV, int N>
+CORR_HD float2 rot8(float2 v) {
+  constexpr float r = 0.70710678118654752f;
+  constexpr int n = N & 7;
+  if (n == 0) return v;
+  if (n == 2) return INV ? make_float2(-v.y, v.x) : make_float2(v.y, -v.x);
+  float cr = (n == 1) ? r : -r, ci = -r;   // n = 1: (r, -r), n = 3: (-r, -r)
+  if (INV) ci = -ci;
+  return make_float2(v.x * cr - v.y * ci, v.x * ci + v.y * cr);
+}
+
+// v[q] = x[q] in, v[k] = X[k] out (natural order both sides)
+template <bool INV>
+CORR_HD void dft8(float2 (&v)[8]) {
+  // decimation in frequency: t_j = x_j + x_{j+4},  u_j = (x_j - x_{j+4}) w8^j
+  float2 t[4], u[4];
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    t[j] = cadd(v[j], v[j + 4]);
+    u[j] = csub(v[j], v[j + 4]);
+  }
+  u[1] = rot8<INV, 1>(u[1]);
+  u[2] = rot8<INV, 2>(u[2]);
+  u[3] = rot8<INV, 3>(u[3]);
+  r4<INV>(t[0], t[1], t[2], t[3]);
+  r4<INV>(u[0], u[1], u[2], u[3]);
+#pragma unroll
+  for (int m = 0; m < 4; ++m) {
+    v[2 * m] = t[m];
+    v[2 * m + 1] = u[m];
+  }
+}
+
+// v[q] = x[q] in, v[k] = X[k] out
+template <bool INV>
+CORR_HD void dft16(float2 (&v)[16]) {
+#pragma unroll
+  for (int q = 0; q < 4; ++q) r4<INV>(v[q], v[q + 4], v[q + 8], v[q + 12]);
+  // now v[q + 4 a] = sum over the q-residue class, index a; twiddle w16^(q a)
+  v[5] = rot16<INV, 1>(v[5]);
+  v[6] = rot16<INV, 2>(v[6]);
+  v[7] = rot16<INV, 3>(v[7]);
+  v[9] = rot16<INV, 2>(v[9]);
+  v[10] = rot16<INV, 4>(v[10]);
+  v[11] = rot16<INV, 6>(v[11]);
+  v[13] = rot16<INV, 3>(v[13]);
+  v[14] = rot16<INV, 6>(v[14]);
+  v[15] = rot16<INV, 9>(v[15]);
+#pragma unroll
+  for (int a = 0; a < 4; ++a) r4<INV>(v[4 * a], v[4 * a + 1], v[4 * a + 2], v[4 * a + 3]);
+  // v[4 a + b] = X[a + 4 b]  ->  natural order
+  float2 w[16];
+#pragma unroll
+  for (int a = 0; a < 4; ++a)
+#pragma unroll
+    for (int b = 0; b < 4; ++b) w[a + 4 * b] = v[4 * a + b];
+#pragma unroll
+  for (int k = 0; k < 16; ++k) v[k] = w[k];
+}
+
+// ---- column passes on a row-major tile [M1][cols], cols = 2^CL ---------------------------------
+// The two upper passes are corr.cuh's radix-16 passes with the twiddle taken at the column-cleared
+// index (the twiddle depends on the row part of j only).
+template <int SUB_LOG2, int CL>
+CORR_HD void dif16_pass_cols(float2* buf, const Tables& t, int tid) {
+#pragma unroll 1
+  for (int rep = 0; rep < 2; ++rep) {
+    const int u = tid + rep * kThreads;
+    const int j = u & ((1 << SUB_LOG2) - 1);
+    int reg[4];
+    pass_addr_init<SUB_LOG2>(u, reg);
+    float2 v[16];
+#pragma unroll
+    for (int q = 0; q < 16; ++q) v[q] = buf[pass_addr<SUB_LOG2>(reg, q)];
+    bfly16_dif(v, pass_twiddle<SUB_LOG2>(t, j & ~((1 << CL) - 1)));
+#pragma unroll
+    for (int a = 0; a < 4; ++a)
+#pragma unroll
+      for (int b = 0; b < 4; ++b) buf[pass_addr<SUB_LOG2>(reg, a + 4 * b)] = v[4 * a + b];
+  }
+}
+
+template <int SUB_LOG2, int CL>
+CORR_HD void dit16_pass_cols(float2* buf, const Tables& t, int tid) {
+#pragma unroll 1
+  for (int rep = 0; rep < 2; ++rep) {
+    const int u = tid + rep * kThreads;
+    const int j = u & ((1 << SUB_LOG2) - 1);
+    int reg[4];
+    pass_addr_init<SUB_LOG2>(u, reg);
+    float2 v[16];
+#pragma unroll
+    for (int a = 0; a < 4; ++a)
+#pragma unroll
+      for (int b = 0; b < 4; ++b) v[4 * a + b] = buf[pass_addr<SUB_LOG2>(reg, a + 4 * b)];
+    bfly16_dit(v, cconj(pass_twiddle<SUB_LOG2>(t, j & ~((1 << CL) - 1))));
+#pragma unroll
+    for (int q = 0; q < 16; ++q) buf[pass_addr<SUB_LOG2>(reg, q)] = v[q];
+  }
+}
+
+// Last forward / first inverse column pass: radix R at stride cols, no twiddles.
+template <bool INV, int R, int CL>
+CORR_HD void last_pass_cols(float2* buf, int tid) {
+  constexpr int n_bfly = kM / R;
+#pragma unroll 1
+  for (int u = tid; u < n_bfly; u += kThreads) {
+    const int c = u & ((1 << CL) - 1);
+    const int base = (((u >> CL) * R) << CL) + c;
+    float2 v[R];
+#pragma unroll
+    for (int q = 0; q < R; ++q) v[q] = buf[swz(base + (q << CL))];
+    if constexpr (R == 2) r2<INV>(v[0], v[1]);
+    if constexpr (R == 4) r4<INV>(v[0], v[1], v[2], v[3]);
+    if constexpr (R == 8) dft8<INV>(v);
+    if constexpr (R == 16) dft16<INV>(v);
+#pragma unroll
+    for (int q = 0; q < R; ++q) buf[swz(base + (q << CL))] = v[q];
+  }
+}
+
+// The column transform of a tile with M1 = 2^Q1 rows (cols = 2^(14 - Q1)) as three steps with a
+// barrier between them (a step may be empty).  Forward: step 0, 1, 2; inverse: step 2, 1, 0 with
+// INV = true.  Output of the forward transform: row position p1 (tile index >> CL) holds frequency
+// col_freq_of_pos(Q1, p1).
+template <int Q1, int STEP, bool INV>
+CORR_HD void col_step(float2* buf, const Tables& t, int tid) {
+  constexpr int CL = 14 - Q1;
+  if constexpr (STEP == 0) {
+    if constexpr (INV) dit16_pass_cols<10, CL>(buf, t, tid);
+    else dif16_pass_cols<10, CL>(buf, t, tid);
+  } else if constexpr (STEP == 1) {
+    if constexpr (Q1 >= 8) {
+      if constexpr (INV) dit16_pass_cols<6, (CL < 6 ? CL : 6)>(buf, t, tid);
+      else dif16_pass_cols<6, (CL < 6 ? CL : 6)>(buf, t, tid);
+    } else {
+      last_pass_cols<INV, (1 << (Q1 - 4)), CL>(buf, tid);   // 64 rows: radix 4, 128 rows: radix 8
+    }
+  } else {
+    if constexpr (Q1 > 8) last_pass_cols<INV, (1 << (Q1 - 8)), CL>(buf, tid);
+  }
+}
+template <int Q1>
+CORR_HD void col_forward(float2* buf, const Tables& t, int tid) {
+  col_step<Q1, 0, false>(buf, t, tid);
+  CORR_SYNC();
+  col_step<Q1, 1, false>(buf, t, tid);
+  CORR_SYNC();
+  col_step<Q1, 2, false>(buf, t, tid);
+}
+template <int Q1>
+CORR_HD void col_inverse(float2* buf, const Tables& t, int tid) {
+  col_step<Q1, 2, true>(buf, t, tid);
+  CORR_SYNC();
+  col_step<Q1, 1, true>(buf, t, tid);
+  CORR_SYNC();
+  col_step<Q1, 0, true>(buf, t, tid);
+}
+
+// frequency held at row position p1 after col_forward (digits of the passes, first pass = lowest)
+CORR_HD int col_freq_of_pos(int q1, int p1) {
+  const int d0 = p1 >> (q1 - 4);
+  if (q1 >= 8) {
+    const int d1 = (p1 >> (q1 - 8)) & 15;
+    const int d2 = p1 & ((1 << (q1 - 8)) - 1);
+    return d0 | (d1 << 4) | (d2 << 8);
+  }
+  const int d2 = p1 & ((1 << (q1 - 4)) - 1);
+  return d0 | (d2 << 4);
+}
+CORR_HD int col_pos_of_freq(int q1, int f) {
+  const int d0 = f & 15;
+  if (q1 >= 8) {
+    const int d1 = (f >> 4) & 15, d2 = f >> 8;
+    return (d0 << (q1 - 4)) | (d1 << (q1 - 8)) | d2;
+  }
+  return (d0 << (q1 - 4)) | (f >> 4);
+}
+
+// ---- rows: 16 contiguous 1024-point transforms per tile (corr.cuh's passes 2..4) -----------------
+template <int STEP, bool INV>
+CORR_HD void row_step(float2* buf, const Tables& t, int tid) {
+  if constexpr (STEP == 0) {
+    if constexpr (INV) dit16_pass_smem<6>(buf, t, tid);
+    else dif16_pass_smem<6>(buf, t, tid);
+  } else if constexpr (STEP == 1) {
+    if constexpr (INV) dit16_pass_smem<2>(buf, t, tid);
+    else dif16_pass_smem<2>(buf, t, tid);
+  } else {
+    r4_pass_smem<INV>(buf, tid);
+  }
+}
+CORR_HD void rows_forward(float2* buf, const Tables& t, int tid) {
+  row_step<0, false>(buf, t, tid);
+  CORR_SYNC();
+  row_step<1, false>(buf, t, tid);
+  CORR_SYNC();
+  row_step<2, false>(buf, t, tid);
+}
+CORR_HD void rows_inverse(float2* buf, const Tables& t, int tid) {
+  row_step<2, true>(buf, t, tid);
+  CORR_SYNC();
+  row_step<1, true>(buf, t, tid);
+  CORR_SYNC();
+  row_step<0, true>(buf, t, tid);
+}
+// position inside a row <-> frequency k2 (radices 16, 16, 4)
+CORR_HD int row_freq_of_pos(int p) { return ((p >> 6) & 15) | (((p >> 2) & 15) << 4) | ((p & 3) << 8); }
+CORR_HD int row_pos_of_freq(int f) { return ((f & 15) << 6) | (((f >> 4) & 15) << 2) | (f >> 8); }
+
+// ---- tables -------------------------------------------------------------------------------------
+// half1024[t] = exp(-i pi t / 1024) (untangle: the k2 part of w_N^k);  fine[t] = exp(-2 pi i t / M),
+// t < M1 (four-step twiddle: w_M^x = tw1024[x >> q1] * fine[x & (M1 - 1)]).
+struct BigTables {
+  const float2* tw1024;
+  const float2* fine32;
+  const float2* half1024;
+  const float2* fine;
+};
+CORR_HD void init_big_tables(float2* half1024, float2* fine, int q1, int tid) {
+  for (int t = tid; t < 1024; t += kThreads) {
+    float s, c;
+    sincospif(-(float)t * (1.0f / 1024.0f), &s, &c);
+    half1024[t] = make_float2(c, s);
+  }
+  const int m1 = 1 << q1;
+  const float inv_half_m = 2.0f / (float)(m1 << 10);   // exp(-2 pi i t / M) = sincospi(-2 t / M)
+  for (int t = tid; t < m1; t += kThreads) {
+    float s, c;
+    sincospif(-(float)t * inv_half_m, &s, &c);
+    fine[t] = make_float2(c, s);
+  }
+}
+// w_M^x, x < M = 2^(q1 + 10)
+CORR_HD float2 step_twiddle(const BigTables& bt, int q1, int x) {
+  return cmul(bt.tw1024[x >> q1], bt.fine[x & ((1 << q1) - 1)]);
+}
+
+// ---- tile geometry --------------------------------------------------------------------------------
+// F2 tile g of a transform with M1 rows: slot s < 8 holds row 8 g + s, slot 8 + s its partner row
+// M1 - (8 g + s); in tile 0 the self-paired rows 0 and M1/2 share the pair (slot 0, slot 8).
+CORR_HD int f2_row_of_slot(int q1, int g, int slot) {
+  const int m1 = 1 << q1;
+  const int k1 = 8 * g + (slot & 7);
+  if (slot < 8) return k1;
+  return k1 == 0 ? (m1 >> 1) : m1 - k1;
+}
+
+// Untangle of one pair of bins (k, M - k): zp = Z[k], zq = Z[M - k], w = w_N^k  ->  2 A[k], 2 A[M - k]
+CORR_HD void untangle_bins(float2 zp, float2 zq, float2 w, float2& hp, float2& hq) {
+  const float2 e = make_float2(zp.x + zq.x, zp.y - zq.y);
+  const float2 d = make_float2(zp.x - zq.x, zp.y + zq.y);
+  const float2 tt = cmul(w, d);
+  hp = make_float2(e.x + tt.y, e.y - tt.x);
+  hq = make_float2(e.x - tt.y, -e.y - tt.x);
+}
+// Inverse packing of the product spectrum: cp = C[k], cq = C[M - k]  ->  Zc[k], Zc[M - k]
+CORR_HD void retangle_bins(float2 cp, float2 cq, float2 w, float2& zp, float2& zq) {
+  const float2 e = make_float2(cp.x + cq.x, cp.y - cq.y);
+  const float2 d = make_float2(cp.x - cq.x, cp.y + cq.y);
+  const float2 tt = cmul(cconj(w), d);
+  zp = make_float2(e.x - tt.y, e.y + tt.x);
+  zq = make_float2(e.x + tt.y, -e.y + tt.x);
+}
+
+// The pairs of an F2 tile, enumerated so that every bin is visited exactly once:
+//   regular slot pairs (s, 8 + s): element (s, p) <-> (8 + s, 1023 - p), p < 1024
+//   tile 0, s = 0:   row 0     : k2 <-> 1024 - k2 for 0 < k2 < 512, specials k2 = 0 (DC + Nyquist of the
+//                                whole transform) and k2 = 512 (its own partner)
+//                    row M1/2  : k2 <-> 1023 - k2 for k2 < 512
+// `visit(ea, eb, w, kind)`: tile element indices (slot * 1024 + position, NOT swizzled) of the two bins
+// (ea == eb for the self-paired bin), the twiddle w_N^k of the first, kind 0 = regular pair,
+// 1 = DC/Nyquist (ea only), 2 = self-paired bin.
+template <class Visit>
+CORR_HD void f2_for_each_pair(const BigTables& bt, int q1, int g, const float2* row_tw, int tid, Visit visit) {
+  // row_tw[slot] = exp(-i pi k1 / M) for the row in that slot
+#pragma unroll 1
+  for (int it = 0; it < 16; ++it) {
+    const int e = tid + it * kThreads;       // 8192 pair slots: s = e >> 10, p = e & 1023
+    const int s = e >> 10, p = e & 1023;
+    if (g == 0 && s == 0) {
+      // 1024 pair slots shared by the two self-paired rows: p < 512 -> row 0, else row M1/2
+      const int k2 = p & 511;
+      if (p < 512) {
+        if (k2 == 0) {
+          visit(row_pos_of_freq(0), row_pos_of_freq(0), make_float2(1.f, 0.f), 1);
+          const int ih = row_pos_of_freq(512);
+          visit(ih, ih, cmul(row_tw[0], bt.half1024[512]), 2);
+        } else {
+          visit(row_pos_of_freq(k2), row_pos_of_freq(1024 - k2), cmul(row_tw[0], bt.half1024[k2]), 0);
+        }
+      } else {
+        const int pa = row_pos_of_freq(k2);
+        visit(8 * 1024 + pa, 8 * 1024 + 1023 - pa, cmul(row_tw[8], bt.half1024[k2]), 0);
+      }
+    } else {
+      const int k2 = row_freq_of_pos(p);
+      visit(s * 1024 + p, (8 + s) * 1024 + 1023 - p, cmul(row_tw[s], bt.half1024[k2]), 0);
+    }
+  }
+}
+
+// scale of the real outputs: unnormalised transforms (M) and factors 2 (A), 2 (B), 2 (retangle)
+CORR_HD float out_scale(int q1) { return 1.0f / (8.0f * (float)(1 << (q1 + 10))); }
+
+
+// ---- per-thread phases of the three kernels (also driven by tests/host_emul/bigfft_emul.cu) ------
+
+// A real signal as the transforms see it: value(t) = 2 x[t] - 1 for t < len (x from a float array
+// or, bit-mask subtitles, hi / -1 per bit), 0 beyond (zero padding up to N).
+struct BigSource {
+  const float* f;
+  const uint32_t* bits;
+  int len;
+  float hi;
+};
+CORR_HD float2 source_pair(const BigSource& s, int n) {   // samples 2 n, 2 n + 1
+  const int t0 = 2 * n;
+  float2 v = make_float2(0.f, 0.f);
+  if (s.bits) {
+    if (t0 < s.len) {
+      const uint32_t w = CORR_LDG(s.bits + (t0 >> 5)) >> (t0 & 31);   // t0 even: both bits in one word
+      v.x = (w & 1u) ? s.hi : -1.f;
+      if (t0 + 1 < s.len) v.y = (w & 2u) ? s.hi : -1.f;
+    }
+  } else {
+    if (t0 < s.len) v.x = 2.f * CORR_LDG(s.f + t0) - 1.f;
+    if (t0 + 1 < s.len) v.y = 2.f * CORR_LDG(s.f + t0 + 1) - 1.f;
+  }
+  return v;
+}
+
+// F1 load: tile cg = columns [cg * cols, (cg + 1) * cols) of the [M1][1024] array z[n] = x[2n] + i x[2n+1].
+// Returns the thread's partial sum of squares.
+CORR_HD float f1_load(float2* buf, const BigSource& src, int q1, int cg, int tid) {
+  const int cl = 14 - q1, c0 = cg << cl;
+  float ss = 0.f;
+  for (int e = tid; e < kM; e += kThreads) {
+    const int n1 = e >> cl, c = e & ((1 << cl) - 1);
+    const float2 v = source_pair(src, (n1 << 10) + c0 + c);
+    ss += v.x * v.x + v.y * v.y;
+    buf[swz(e)] = v;
+  }
+  return ss;
+}
+// F1 store: four-step twiddle w_M^(n2 k1), rows in natural k1 order.
+CORR_HD void f1_store(const float2* buf, const BigTables& bt, int q1, int cg, int tid, float2* g) {
+  const int cl = 14 - q1, c0 = cg << cl, mmask = (1 << (q1 + 10)) - 1;
+  for (int e = tid; e < kM; e += kThreads) {
+    const int p1 = e >> cl, n2 = c0 + (e & ((1 << cl) - 1));
+    const int k1 = col_freq_of_pos(q1, p1);
+    g[((size_t)k1 << 10) + n2] = cmul(buf[swz(e)], step_twiddle(bt, q1, (int)(((long long)n2 * k1) & mmask)));
+  }
+}
+
+// F2 load / store of the 16 rows of tile g (slot order, see f2_row_of_slot).
+CORR_HD void f2_load(float2* buf, int q1, int g, int tid, const float2* src) {
+  for (int e = tid; e < kM; e += kThreads)
+    buf[swz(e)] = CORR_LDG(src + ((size_t)f2_row_of_slot(q1, g, e >> 10) << 10) + (e & 1023));
+}
+CORR_HD void f2_store(const float2* buf, int q1, int g, int tid, float2* dst) {
+  for (int e = tid; e < kM; e += kThreads)
+    dst[((size_t)f2_row_of_slot(q1, g, e >> 10) << 10) + (e & 1023)] = buf[swz(e)];
+}
+// row_tw[slot] = exp(-i pi k1 / M): threads 0..15
+CORR_HD void f2_row_twiddles(float2* row_tw, int q1, int g, int tid) {
+  if (tid < 16) {
+    float sn, cs;
+    sincospif(-(float)f2_row_of_slot(q1, g, tid) / (float)(1 << (q1 + 10)), &sn, &cs);
+    row_tw[tid] = make_float2(cs, sn);
+  }
+}
+// Reference: rows (already transformed, position order) -> packed real spectrum 2 B[k], in place.
+CORR_HD void f2_untangle_inplace(float2* buf, const BigTables& bt, int q1, int g, const float2* row_tw, int tid) {
+  f2_for_each_pair(bt, q1, g, row_tw, tid, [&](int ea, int eb, float2 w, int kind) {
+    const int ia = swz(ea), ib = swz(eb);
+    const float2 zp = buf[ia], zq = buf[ib];
+    if (kind == 1) {
+      buf[ia] = make_float2(2.f * (zp.x + zp.y), 2.f * (zp.x - zp.y));   // DC, Nyquist
+      return;
+    }
+    float2 hp, hq;
+    untangle_bins(zp, zq, w, hp, hq);
+    buf[ia] = hp;
+    if (kind == 0) buf[ib] = hq;
+  });
+}
+// Subtitles: rows (transformed) -> conj(2 A) * (2 B) -> packed for the inverse transform, in place.
+// spec = the stored reference spectrum of the same transform geometry (tile layout [k1][position]).
+CORR_HD void f2_product_inplace(float2* buf, const BigTables& bt, int q1, int g, const float2* row_tw, int tid,
+                                const float2* spec) {
+  f2_for_each_pair(bt, q1, g, row_tw, tid, [&](int ea, int eb, float2 w, int kind) {
+    const int ia = swz(ea), ib = swz(eb);
+    const float2 zp = buf[ia], zq = buf[ib];
+    const float2 bp = CORR_LDG(spec + ((size_t)f2_row_of_slot(q1, g, ea >> 10) << 10) + (ea & 1023));
+    if (kind == 1) {
+      const float c0 = 2.f * (zp.x + zp.y) * bp.x, cm = 2.f * (zp.x - zp.y) * bp.y;
+      buf[ia] = make_float2(c0 + cm, c0 - cm);
+      return;
+    }
+    float2 hp, hq;
+    untangle_bins(zp, zq, w, hp, hq);
+    const float2 cp = cmul_conj_a(hp, bp);
+    float2 cq = cp;
+    if (kind == 0)
+      cq = cmul_conj_a(hq, CORR_LDG(spec + ((size_t)f2_row_of_slot(q1, g, eb >> 10) << 10) + (eb & 1023)));
+    float2 np, nq;
+    retangle_bins(cp, cq, w, np, nq);
+    buf[ia] = np;
+    if (kind == 0) buf[ib] = nq;
+  });
+}
+// F2 (subtitles) store after the inverse row transform: conjugate four-step twiddle.
+CORR_HD void f2_store_twiddled(const float2* buf, const BigTables& bt, int q1, int g, int tid, float2* dst) {
+  const int mmask = (1 << (q1 + 10)) - 1;
+  for (int e = tid; e < kM; e += kThreads) {
+    const int k1 = f2_row_of_slot(q1, g, e >> 10), n2 = e & 1023;
+    dst[((size_t)k1 << 10) + n2] =
+        cmul(buf[swz(e)], cconj(step_twiddle(bt, q1, (int)(((long long)n2 * k1) & mmask))));
+  }
+}
+
+// F3 load: columns of the k1-major array into row positions (digit-reversed for the inverse passes).
+CORR_HD void f3_load(float2* buf, int q1, int cg, int tid, const float2* g) {
+  const int cl = 14 - q1, c0 = cg << cl;
+  for (int e = tid; e < kM; e += kThreads) {
+    const int k1 = col_freq_of_pos(q1, e >> cl);
+    buf[swz(e)] = CORR_LDG(g + ((size_t)k1 << 10) + c0 + (e & ((1 << cl) - 1)));
+  }
+}
+// F3 store: c[2n], c[2n+1] = re, im of z[n]; score index m = (lag + S) mod N (offset o = m - S).
+// mx: maximum over the surviving window [m_lo, m_hi]; cn: sum of squares of everything written.
+CORR_HD void f3_store(const float2* buf, int q1, int cg, int tid, float* scores, int S, int m_lo, int m_hi,
+                      float& mx, float& cn) {
+  const int cl = 14 - q1, c0 = cg << cl;
+  const int nmask = (2 << (q1 + 10)) - 1;
+  const float sc = out_scale(q1);
+  for (int e = tid; e < kM; e += kThreads) {
+    const int n = ((e >> cl) << 10) + c0 + (e & ((1 << cl) - 1));
+    const float2 z = buf[swz(e)];
+    const float v0 = z.x * sc, v1 = z.y * sc;
+    const int m0 = (2 * n + S) & nmask, m1 = (2 * n + 1 + S) & nmask;
+    scores[m0] = v0;
+    scores[m1] = v1;
+    cn += v0 * v0 + v1 * v1;
+    if (m0 >= m_lo && m0 <= m_hi) mx = fmaxf(mx, v0);
+    if (m1 >= m_lo && m1 <= m_hi) mx = fmaxf(mx, v1);
+  }
+}
+
+}  // namespace bigfft

@@ -22,34 +22,11 @@
 
 #include "common.cuh"
 #include "corr.cuh"
+#include "corr_jobs.cuh"
 
 namespace {
 
 using namespace corr;
-
-constexpr int kCandMax = 32;
-constexpr int kRescoreSeg = 16;
-// Nomination threshold tau ("Round-off bound"): every offset whose fp32 score
-// is within tau of the fp32 maximum is re-scored exactly, with
-//     tau = u * (kTauFwd * sqrt(Es*Er) + (kTauInv + n_split - 1) * ||c||_2),   u = 2^-24,
-// a first-order WORST-CASE bound on |fp32 score - exact score| (all rounding errors aligned):
-//   kTauFwd: both forward transforms (first pass 95u: the twiddle w^k of the depth-4 product chain
-//            carries k <= 15 times the 5.7u error of the two-table base twiddle; passes 2-4
-//            32u + 22u + 3u; untangle 16u) = 2 x 168u, spectral product 3u, accumulation over
-//            <= 64 blocks in fp32 <= 63u (more blocks: see window_max_kernel), retangle 16u -> <= 418u,
-//            rounded up to 512 for the second-order terms;
-//   kTauInv: the inverse transform is backward stable in the 2-norm, |error[m]| <= eps_inv*||c||_2
-//            with eps_inv = 16u + 3u + 22u + 32u + 95u = 168u -> 192; ||c||_2 is the norm of the
-//            tile's whole inverse-transform output, computed by the kernel (it exceeds sqrt(Es*Er)
-//            only for signals with a large mean, whose correlation is a broad ramp);
-//   n_split - 1: fp32 addition of the partial score arrays of a split job.
-// Measured on random, constant, periodic, sparse and wide-dynamic-range inputs the error stays
-// below 12 u sqrt(Es*Er) (tests/test_host_cpu.py::test_roundoff_bound_*): the bound has > 40x slack,
-// and costs nothing on real data, where the runner-up is thousands of units below the peak.
-constexpr float kU = 5.9604645e-8f;
-constexpr float kTauFwd = 512.0f;
-constexpr float kTauInv = 192.0f;
-constexpr int kTauBlocks = 64;  // block count covered by kTauFwd
 
 struct SpecItem {      // one reference block to transform
   long long ref_off;   // element offset of the pair's reference signal
@@ -65,19 +42,6 @@ struct SubJob {        // one (pair, ratio, offset tile)
   // bit-mask mode (b2_sync_batch): the subtitle signal is one bit per frame (raster_bits_kernel)
   long long bits_off;  // word offset of this (pair, ratio)'s speech bit mask
   float hi;            // 2*min(1/ratio, 1) - 1: value of a frame inside a cue after x -> 2x-1
-};
-
-struct SelJob {        // one (pair, ratio)
-  long long ref_off, sub_off, score_off;
-  int R, S, o_first;   // offset of scores[score_off]
-  int m_lo, m_hi;      // valid window of m (inclusive); m_lo > m_hi: nothing survives
-  int energy_slot, n_tiles;
-  int n_split;         // partial score arrays per tile (small batches split the block range over CTAs)
-  int out_index;       // b*K + k
-  int kind;            // 0 normal, 1 empty input, 2 everything masked
-  int masked_offset;   // offset reported when kind == 2
-  long long bits_off;  // >= 0: the subtitle signal is a bit mask (one bit per frame)
-  float sub_level;     // value of a frame inside a cue, min(1/ratio, 1) as float32 (bit-mask mode)
 };
 
 // bit-mask mode: the speech bits of the current and the next block (kP/32 words each) sit behind
@@ -699,9 +663,11 @@ int b2i_align_launch(b2_ctx* h, const float* d_ref, const int64_t* ref_off, cons
     for (size_t j = 0; j < J; ++j)
       bits_off[j + 1] = bits_off[j] + ((sub_off[j + 1] - sub_off[j]) + kP) / 32 + 1;
   std::vector<SelJob> sel(J);
+  std::vector<long long> idx_lo(J, 0), idx_hi(J, 0), n_pad(J, 0);
   struct PairPlan { long long o_min, o_max; int n_tiles; bool any; };
   std::vector<PairPlan> pp(B);
   long long max_w = 1;
+  bool big_ok = true;   // every live job's padded length suits the large-window path
   for (int b = 0; b < B; ++b) {
     const long long R = ref_off[b + 1] - ref_off[b];
     if (R < 0 || R > 0x3fffffff) B2_FAIL(h, B2_ERR_BAD_ARG, "align: bad reference length at %d", b);
@@ -743,6 +709,10 @@ int b2i_align_launch(b2_ctx* h, const float* d_ref, const int64_t* ref_off, cons
         continue;
       }
       const long long o_lo = N - S - hi, o_hi = N - 1 - S - lo;  // aligners.py:47
+      idx_lo[j] = lo;
+      idx_hi[j] = hi;
+      n_pad[j] = N;
+      if (N < (1LL << (bigfft_min_log2n())) || N > (1LL << bigfft_max_log2n())) big_ok = false;
       s.kind = 0;
       s.m_lo = (int)o_lo;  // temporarily absolute offsets; rebased below
       s.m_hi = (int)o_hi;
@@ -771,6 +741,31 @@ int b2i_align_launch(b2_ctx* h, const float* d_ref, const int64_t* ref_off, cons
                                     cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytesBits));
     B2_CUDA(h, cudaFuncSetAttribute(sub_correlate_bits_regacc_kernel,
                                     cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytesBits));
+  }
+  void* d_cand;
+  B2_TRY(b2i_ws(h, b2_ctx::WS_CAND, J * kCandMax * (8 * kRescoreSeg + 8) + J * 12 + 64, &d_cand));
+  B2CandBuffers cb;
+  cb.cand_partial = (double*)d_cand;
+  cb.job_stat = (float2*)(cb.cand_partial + J * kCandMax * kRescoreSeg);
+  cb.cand_off = (int*)(cb.job_stat + J);
+  cb.cand_cnt = cb.cand_off + J * kCandMax;
+  cb.work_list = cb.cand_cnt + J;
+  cb.work_count = cb.work_list + J * kCandMax;
+  if (J >= (1u << 26)) B2_FAIL(h, B2_ERR_UNSUPPORTED, "align: B*K too large for one call");
+
+  // Large windows (FFTAligner's default max_offset_samples=None, or a mask wider than a few tiles):
+  // the overlap-save path would recompute every block for every 16 385-offset tile; one padded-length
+  // FFT per signal (four-step, bigfft.cu) is cheaper from kBigMinTiles tiles on.
+  // B2_ALIGN_PATH=tiled|big: test / A-B knob.
+  bool use_big = big_ok && max_w > (long long)kBigMinTiles * (kP / 2 + 1);
+  if (const char* e = getenv("B2_ALIGN_PATH")) {
+    if (!strcmp(e, "tiled")) use_big = false;
+    if (!strcmp(e, "big") && big_ok) use_big = true;
+  }
+  if (use_big) {
+    const SelJob* d_sel_big = nullptr;
+    B2_TRY(b2i_align_big(h, d_ref, d_sub, d_bits, B, K, sel, idx_lo, idx_hi, n_pad, winner_only, cb, &d_sel_big));
+    return b2i_rescore_pick(h, d_sel_big, J, d_ref, d_sub, d_bits, cb, d_score, d_offset, d_status);
   }
 
   // score buffers + per-(pair,ratio) bookkeeping
@@ -813,18 +808,11 @@ int b2i_align_launch(b2_ctx* h, const float* d_ref, const int64_t* ref_off, cons
     }
   }
 
-  void *d_scores, *d_cand;
+  void* d_scores;
   B2_TRY(b2i_ws(h, b2_ctx::WS_SCORES, (size_t)(score_total + 16) * 4 + (size_t)(energy_total + 2) * 16,
                 &d_scores));
   float* scores = (float*)d_scores;
   float4* job_energy = (float4*)((char*)d_scores + (((size_t)(score_total + 16) * 4 + 15) & ~size_t(15)));
-  B2_TRY(b2i_ws(h, b2_ctx::WS_CAND, J * kCandMax * (8 * kRescoreSeg + 8) + J * 12 + 64, &d_cand));
-  double* cand_partial = (double*)d_cand;
-  float2* job_stat = (float2*)(cand_partial + J * kCandMax * kRescoreSeg);
-  int* cand_off = (int*)(job_stat + J);
-  int* cand_cnt = cand_off + J * kCandMax;
-  int* work_list = cand_cnt + J;
-  int* work_count = work_list + J * kCandMax;
 
   B2_CUDA(h, cudaFuncSetAttribute(ref_spectra_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                   (int)kSmemBytes));
@@ -932,22 +920,29 @@ int b2i_align_launch(b2_ctx* h, const float* d_ref, const int64_t* ref_off, cons
   B2_TRY(flush());
 
   B2Range range_sel("b2:select+rescore+pick");
+
   MetaArena a;
   B2_TRY(b2i_meta_begin(h, &a, J * sizeof(SelJob) + 256));
   const SelJob* d_sel = (const SelJob*)b2i_meta_put(&a, sel.data(), J * sizeof(SelJob));
   B2_TRY(b2i_meta_commit(&a));
-  if (J >= (1u << 26)) B2_FAIL(h, B2_ERR_UNSUPPORTED, "align: B*K too large for one call");
-  B2_CUDA(h, cudaMemsetAsync(work_count, 0, sizeof(int), h->stream));
-  window_max_kernel<<<(unsigned)J, 256, 0, h->stream>>>(d_sel, scores, job_energy, job_stat, Wt);
+  B2_CUDA(h, cudaMemsetAsync(cb.work_count, 0, sizeof(int), h->stream));
+  window_max_kernel<<<(unsigned)J, 256, 0, h->stream>>>(d_sel, scores, job_energy, cb.job_stat, Wt);
   B2_CHECK_LAUNCH(h, "window_max_kernel");
-  select_candidates_kernel<<<(unsigned)J, 256, 0, h->stream>>>(d_sel, scores, job_stat, K, winner_only,
-                                                                cand_off, cand_cnt, work_list, work_count);
+  select_candidates_kernel<<<(unsigned)J, 256, 0, h->stream>>>(d_sel, scores, cb.job_stat, K, winner_only,
+                                                                cb.cand_off, cb.cand_cnt, cb.work_list,
+                                                                cb.work_count);
   B2_CHECK_LAUNCH(h, "select_candidates_kernel");
+  return b2i_rescore_pick(h, d_sel, J, d_ref, d_sub, d_bits, cb, d_score, d_offset, d_status);
+}
+
+int b2i_rescore_pick(b2_ctx* h, const SelJob* d_sel, size_t J, const float* d_ref, const float* d_sub,
+                     const uint32_t* d_bits, const B2CandBuffers& cb, double* d_score, int32_t* d_offset,
+                     int32_t* d_status) {
   rescore_kernel<<<(unsigned)(h->sm_count * 8), 256, 0, h->stream>>>(
-      d_sel, d_ref, d_sub, cand_off, work_list, work_count, d_bits, cand_partial);
+      d_sel, d_ref, d_sub, cb.cand_off, cb.work_list, cb.work_count, d_bits, cb.cand_partial);
   B2_CHECK_LAUNCH(h, "rescore_kernel");
-  pick_kernel<<<(unsigned)((J + 127) / 128), 128, 0, h->stream>>>(d_sel, (int)J, cand_off, cand_cnt,
-                                                                   cand_partial, job_stat, d_score,
+  pick_kernel<<<(unsigned)((J + 127) / 128), 128, 0, h->stream>>>(d_sel, (int)J, cb.cand_off, cb.cand_cnt,
+                                                                   cb.cand_partial, cb.job_stat, d_score,
                                                                    d_offset, d_status);
   B2_CHECK_LAUNCH(h, "pick_kernel");
   return B2_OK;

@@ -57,6 +57,31 @@ def shifted_pair(n: int, shift: int = 1234, seed: int = 0):
     return ref, sub
 
 
+# Wide-window alignments (large FFT path): lengths, shift, subtitle level, masks to run.
+WIDE_CASES = [
+    dict(seed=1, R=70000, S=60000, shift=4321, level=1.0, mos_list=[None, 40000]),
+    dict(seed=2, R=200000, S=9000, shift=-150000, level=1.0, mos_list=[None]),       # R >> S, negative offset... (sub late in ref)
+    dict(seed=3, R=9000, S=200000, shift=120000, level=0.96, mos_list=[None, 150000]),   # S >> R, float level
+    dict(seed=4, R=131000, S=131100, shift=77, level=1.0, mos_list=[None]),            # R + S just above 2^18
+    dict(seed=5, R=131072, S=131072, shift=-5, level=0.5, mos_list=[None, 70000]),      # R + S == 2^18 exactly
+    dict(seed=6, R=300000, S=280000, shift=None, level=1.0, mos_list=[None]),           # unrelated signals
+]
+
+
+def wide_pair(seed, R, S, shift, level, mos_list=None):
+    """ref = rand > 0.55; sub[j] = level * ref[j + offset] with offset = -shift ... i.e. the subtitles are the
+    reference delayed by ``shift`` frames (negative: advanced), or independent noise when shift is None."""
+    rng = np.random.RandomState(seed)
+    ref = (rng.rand(R) > 0.55).astype(float)
+    if shift is None:
+        sub = (rng.rand(S) > 0.5).astype(float) * level
+    else:
+        idx = np.arange(S) - shift
+        ok = (idx >= 0) & (idx < R)
+        sub = np.where(ok, ref[np.clip(idx, 0, R - 1)], (rng.rand(S) > 0.5).astype(float)) * level
+    return ref, sub
+
+
 def scaled_signal(sub: np.ndarray, sf: float) -> np.ndarray:
     """Nearest-neighbour resampling of a 100 Hz signal by a framerate ratio (the construction
     the reference's own multi-segment test uses to emulate SubtitleScaler on a raw signal)."""

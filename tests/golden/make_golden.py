@@ -99,12 +99,22 @@ def gen_alignment(mods, out):
     out["small"] = small
 
     shifted = []
-    for n in (6000, 60000, 360000, 720000):
+    for n in (6000, 60000, 360000, 720000, 1440000):
         ref, sub = cases.shifted_pair(n)
-        for mos in (6000, None):
+        for mos in (6000, None) + ((100000,) if n >= 360000 else ()):
             score, off = al.FFTAligner(mos).fit_transform(ref, sub, get_score=True)
             shifted.append({"n": n, "mos": mos, "offset": int(off), "score": jf(score)})
     out["shifted"] = shifted
+
+    # wide-window cases (FFTAligner's default max_offset_samples=None and masks wider than a few
+    # overlap-save tiles): lopsided lengths, non-binary levels, lengths that straddle a power of two
+    wide = []
+    for c in cases.WIDE_CASES:
+        ref, sub = cases.wide_pair(**c)
+        for mos in c["mos_list"]:
+            score, off = al.FFTAligner(mos).fit_transform(ref, sub, get_score=True)
+            wide.append({"case": c, "mos": mos, "offset": int(off), "score": jf(score)})
+    out["wide"] = wide
 
     empties = []
     for ref, sub in (([], [1, 0, 1]), ([1, 0, 1], []), ([], [])):

@@ -408,3 +408,68 @@ def test_pipeline_maker_keeps_the_reference_signature():
                          "parser"]
     with pytest.raises(ValueError):
         make_subtitle_speech_pipeline("srt")   # a caller written for the reference: no silent mis-binding
+
+
+# ---- large-window path: the four-step FFT kernels emulated on the CPU (bigfft.cuh) --------------------
+
+def _emulate_big(ref, sub, q1, mode=0):
+    tmp = os.path.join(ROOT, "tests", "host_emul")
+    fin, fout = os.path.join(tmp, "_bin.bin"), os.path.join(tmp, "_bout.bin")
+    with open(fin, "wb") as f:
+        f.write(struct.pack("4i", len(ref), len(sub), q1, mode))
+        f.write(np.asarray(ref, np.float32).tobytes())
+        f.write(np.asarray(sub, np.float32).tobytes())
+    subprocess.check_call([os.path.join(tmp, "bigfft_emul"), fin, fout])
+    out = np.fromfile(fout, dtype=np.float32)
+    os.remove(fin)
+    os.remove(fout)
+    n = 1 << (q1 + 11)
+    return out[:n].astype(np.float64), float(out[n]), float(out[n + 1]), float(out[n + 2])
+
+
+def _direct_big(ref, sub, n):
+    r, s = 2 * np.asarray(ref, np.float64) - 1, 2 * np.asarray(sub, np.float64) - 1
+    full = np.fft.irfft(np.conj(np.fft.rfft(s, n)) * np.fft.rfft(r, n), n)   # full[o mod n] = score(o)
+    return full[(np.arange(n) - len(s)) % n]                                 # scores[m], offset o = m - S
+
+
+@pytest.mark.parametrize("q1", [6, 7, 8, 9, 10, 11, 12])
+def test_bigfft_emulation_all_transform_sizes(built, q1):
+    """F1 (columns + four-step twiddle) -> F2 (rows, untangle, product, inverse rows) -> F3 (inverse
+    columns) for every supported M1 = 2^q1, float and bit-mask subtitle signals, against np.fft."""
+    n = 1 << (q1 + 11)
+    rng = np.random.RandomState(q1)
+    R, S = int(n * 0.45), int(n * 0.5) - 3
+    ref = (rng.rand(R) > 0.5).astype(np.float32)
+    sub = np.concatenate([np.zeros(777, np.float32), ref])[:S]
+    for mode, level in ((0, 0.96), (1, 1.0)):
+        s = sub * np.float32(level)
+        got, es, er, cn = _emulate_big(ref, s, q1, mode)
+        want = _direct_big(ref, s, n)
+        err = np.abs(got - want).max()
+        assert err <= _tau(es, er, cn) / 4, (q1, mode, err)
+        assert err <= 16 * 2.0 ** -24 * np.sqrt(es * er)
+        assert np.argmax(got) == np.argmax(want) == len(s) - 777   # offset = m - S = -777
+
+
+@pytest.mark.parametrize("q1,R,S", [(6, 1, 1), (6, 100, 130972), (6, 65536, 65536), (7, 5, 200000), (6, 70001, 3),
+                                    (8, 262143, 1), (9, 400001, 600000)])
+def test_bigfft_emulation_edge_lengths(built, q1, R, S):
+    n = 1 << (q1 + 11)
+    rng = np.random.RandomState(R + S)
+    ref = (rng.rand(R) > 0.3).astype(np.float32)
+    sub = (rng.rand(S) > 0.6).astype(np.float32)
+    got, es, er, cn = _emulate_big(ref, sub, q1, 1)
+    want = _direct_big(ref, sub, n)
+    assert np.abs(got - want).max() <= _tau(es, er, cn) / 4
+    assert es == S and er == R   # +-1 signals: the energies are the lengths
+
+
+def test_bigfft_roundoff_adversarial(built):
+    for fam_r, fam_s, seed in (("ones", "ones", 1), ("period_block", "period_block", 2), ("sparse", "random", 3),
+                               ("wide", "wide", 4), ("ramp", "period2", 5), ("zeros", "ones", 6)):
+        rng = np.random.RandomState(seed)
+        ref, sub = _family(fam_r, 120000, rng), _family(fam_s, 130000, rng, level=0.96)
+        got, es, er, cn = _emulate_big(ref, sub, 7, 0)
+        want = _direct_big(ref, sub, 1 << 18)
+        assert np.abs(got - want).max() <= _tau(es, er, cn) / 4, (fam_r, fam_s)

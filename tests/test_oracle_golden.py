@@ -71,6 +71,19 @@ def test_shifted_pairs(golden, gf, n):
         assert _close(ao.exact_score(ref, sub, off), n - 1234, abs_=0)
 
 
+def test_wide_window_cases(golden, gf):
+    """Oracle vs the reference on the wide-window fixtures (unmasked / very wide masks; lopsided
+    lengths, float levels, R + S at and just above a power of two) that pin the large-FFT path."""
+    for c in golden["wide"]:
+        kw = dict(c["case"])
+        kw.pop("mos_list")
+        ref, sub = cases.wide_pair(**kw)
+        score, off = ao.fft_align(ref, sub, c["mos"])
+        assert off == c["offset"], c
+        assert _close(score, gf(c["score"]))
+        assert _close(ao.exact_score(ref, sub, off), gf(c["score"]), rel=1e-9)
+
+
 def test_empty_inputs_raise(golden):
     for c in golden["empty"]:
         assert c["raises"] and "empty speech data" in c["raises"]
