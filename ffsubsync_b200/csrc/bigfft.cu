@@ -218,6 +218,13 @@ __global__ void __launch_bounds__(256) big_stat_kernel(const BigJob* __restrict_
   }
 }
 
+// jobs that never reach big_stat_kernel (empty input, everything masked) must not look like winners
+// to their siblings' winner-only test
+__global__ void big_init_stat_kernel(float2* __restrict__ job_stat, int n) {
+  const int j = blockIdx.x * blockDim.x + threadIdx.x;
+  if (j < n) job_stat[j] = make_float2(-INFINITY, 0.f);
+}
+
 // The cut of a job: fp32 maximum minus tau; with winner_only a ratio that provably cannot be the
 // pair's best keeps only its fp32 argmax (same rule as select_candidates_kernel in corr.cu).
 __device__ __forceinline__ float job_cut(const float2* __restrict__ job_stat, int j, int K, int winner_only,
@@ -428,13 +435,9 @@ int b2i_align_big(b2_ctx* h, const float* d_ref, const float* d_sub, const uint3
   B2_TRY(b2i_meta_commit(&a));
   *d_sel_out = d_sel;
   B2_CUDA(h, cudaMemsetAsync(cb.work_count, 0, sizeof(int), h->stream));
-  // jobs that are not live (empty / fully masked) have no candidates
-  {
-    std::vector<int> zero_jobs;
-    for (size_t j = 0; j < J; ++j)
-      if (sel[j].kind != 0) zero_jobs.push_back((int)j);
-    if (!zero_jobs.empty()) B2_CUDA(h, cudaMemsetAsync(cb.cand_cnt, 0, J * sizeof(int), h->stream));
-  }
+  B2_CUDA(h, cudaMemsetAsync(cb.cand_cnt, 0, J * sizeof(int), h->stream));   // jobs that are not live: no candidates
+  big_init_stat_kernel<<<(unsigned)((J + 255) / 256), 256, 0, h->stream>>>(cb.job_stat, (int)J);
+  B2_CHECK_LAUNCH(h, "big_init_stat_kernel");
   if (groups.empty()) return B2_OK;
 
   void *d_g, *d_s;
