@@ -159,9 +159,16 @@ def _oracle_check_worker(index):
                           for i in range(0, len(pcm), chunk)])
     subs = [ro.rasterize(starts, ends, None, SAMPLE_RATE, 0, r)[0] for r in ratios]
     mos = ao.max_offset_samples_of(SAMPLE_RATE, MAX_OFFSET_SECONDS)
-    per_ratio = [ao.fft_align(ref, sub, mos) for sub in subs]
+    per_ratio, ties = [], 0
+    for sub in subs:
+        conv = ao.correlation(ref, sub)
+        lo, hi = ao.surviving_index_range(len(conv), len(sub), mos)
+        idx = lo + int(np.argmax(conv[lo:hi]))
+        per_ratio.append((float(conv[idx]), len(conv) - 1 - idx - len(sub)))
+        # offsets of this ratio whose score equals the maximum to within the float64 FFT's round-off
+        ties += int(np.count_nonzero(conv[lo:hi] >= conv[idx] - 1e-6)) - 1
     k = ao.max_score_select(per_ratio, mos)
-    return per_ratio, k
+    return per_ratio, k, ties
 
 
 def verify_against_oracle(bs, pairs, pcm_d, pcm_off, ratios, n_sample, seed):
@@ -199,7 +206,8 @@ def verify_against_oracle(bs, pairs, pcm_d, pcm_off, ratios, n_sample, seed):
         res = pool.map(_oracle_check_worker, range(len(jobs)), chunksize=1)
     _CHECK_JOBS[:] = []
     bad, max_rel = [], 0.0
-    for b, (per_ratio, k) in zip(sample, res):
+    n_ties = sum(r[2] for r in res)
+    for b, (per_ratio, k, _) in zip(sample, res):
         for kk, (sc, off) in enumerate(per_ratio):
             rel = abs(a_score[b, kk] - sc) / max(abs(sc), 1.0)
             max_rel = max(max_rel, rel)
@@ -211,6 +219,7 @@ def verify_against_oracle(bs, pairs, pcm_d, pcm_off, ratios, n_sample, seed):
             bad.append((b, "winner", int(full["best_k"][b]), k, int(full["best_offset"][b]), int(off)))
     return {"ok": (not bad) and same_winner, "pairs_checked": sample, "ratios_checked": K,
             "winner_only_equals_all_ratios": same_winner, "max_score_rel_err": max_rel,
+            "exact_ties_in_sample": n_ties,
             "mismatches": bad[:8], "oracle_seconds": round(time.perf_counter() - t0, 1),
             "what": "b2_sync_batch on the full batch vs oracle (numpy detector + complex128 FFTAligner + "
                     "MaxScoreAligner) on a seeded sample; offsets exact, scores <= 1e-5 relative"}
@@ -516,6 +525,34 @@ def _cpu_setup(ratios):
                       ratios=list(ratios), expect=1234)
 
 
+def available_cores():
+    """Host cores this process may actually use: the container's CPU quota (cgroup v2 cpu.max, v1
+    cfs_quota) when there is one, else the affinity mask.  On the bench pod os.cpu_count() says 128
+    but cpu.max is "1600000 100000" = 16 cores: 16 workers give 4.9 alignments/s, 32 give 3.1, 128
+    give 1.9 (profiles/r2a_cpu_sweep.json) - oversubscribing the quota only adds context switches.
+    B2_CPU_WORKERS overrides."""
+    if os.environ.get("B2_CPU_WORKERS"):
+        return max(1, int(os.environ["B2_CPU_WORKERS"])), "B2_CPU_WORKERS"
+    n = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+    src = "sched_getaffinity"
+    try:
+        with open("/sys/fs/cgroup/cpu.max") as fh:
+            quota, period = fh.read().split()
+        if quota != "max":
+            q = max(1, int(np.ceil(int(quota) / float(period))))
+            if q < n:
+                n, src = q, "cgroup cpu.max %s/%s" % (quota, period)
+    except (OSError, ValueError):
+        try:
+            with open("/sys/fs/cgroup/cpu/cpu.cfs_quota_us") as fq, open("/sys/fs/cgroup/cpu/cpu.cfs_period_us") as fp:
+                quota, period = int(fq.read()), int(fp.read())
+            if quota > 0 and int(np.ceil(quota / period)) < n:
+                n, src = int(np.ceil(quota / period)), "cgroup cfs quota"
+        except (OSError, ValueError):
+            pass
+    return max(1, n), src
+
+
 def cpu_pass(n_pairs, cores):
     import multiprocessing as mp
     t0 = time.perf_counter()
@@ -533,14 +570,12 @@ def cpu_baseline_sample(K, ratios, budget_pairs=None):
     for v in ("OMP_NUM_THREADS", "MKL_NUM_THREADS", "OPENBLAS_NUM_THREADS"):
         os.environ[v] = "1"
     cores = os.cpu_count() or 1
-    # worker processes: measured on the 128-core bench host, 16 workers give 4.9 alignments/s, 32 give 3.3 and
-    # 128 workers 2.0 (page-fault / memory-bandwidth contention of the numpy path), so more
-    # workers do not help the CPU; B2_CPU_WORKERS overrides
-    used = max(1, min(cores, int(os.environ.get("B2_CPU_WORKERS", "16"))))
+    used, quota_src = available_cores()
     _cpu_setup(ratios)
     n_pairs = budget_pairs or used
     rate, dt = cpu_pass(n_pairs, used)
-    return {"value": rate, "unit": UNIT, "cores": used, "host_cores": cores, "kind": "port",
+    return {"value": rate, "unit": UNIT, "cores": used, "host_cores": cores, "cores_source": quota_src,
+            "kind": "port",
             "sample": "%d two-hour pairs (one per worker process), K=%d ratios, VAD + aligner, %.1f s wall"
                       % (n_pairs, K, dt)}
 
@@ -555,10 +590,7 @@ def run_reference(args):
     for v in ("OMP_NUM_THREADS", "MKL_NUM_THREADS", "OPENBLAS_NUM_THREADS"):
         os.environ[v] = "1"
     cores = os.cpu_count() or 1
-    # worker processes: measured on the 128-core bench host, 16 workers give 4.9 alignments/s, 32 give 3.3 and
-    # 128 workers 2.0 (page-fault / memory-bandwidth contention of the numpy path), so more
-    # workers do not help the CPU; B2_CPU_WORKERS overrides
-    used = max(1, min(cores, int(os.environ.get("B2_CPU_WORKERS", "16"))))
+    used, quota_src = available_cores()
     _cpu_setup(ratios)
     per_step = used
     for _ in range(min(args.warmup, 1)):   # one warm-up pass is enough for a CPU pool; bounded runtime
@@ -576,7 +608,8 @@ def run_reference(args):
         "config": {"workload": "same as the GPU arm: 2 h pairs, 16 kHz PCM -> energy/ZCR detector (numpy "
                                "restatement) -> FFTAligner (numpy complex128, aligners.py:50-80) over K ratios, "
                                "max_offset_seconds=60", "pairs_per_step": per_step, "ratios": K},
-        "cpu_baseline": {"value": value, "unit": UNIT, "cores": used, "host_cores": cores, "kind": "port",
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": used, "host_cores": cores,
+                         "cores_source": quota_src, "kind": "port",
                          "sample": "%d two-hour pairs per step, one per worker process" % per_step},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "note": "the reference is pure Python and cannot travel to the GPU box; this is the oracle port of "

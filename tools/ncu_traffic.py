@@ -2,7 +2,11 @@
 """DRAM traffic per launch of vad_energy_zcr_kernel from an `ncu --set full` capture ->
 profiles/r2_vad_traffic.json (bench.py reads it for roofline.traffic instead of a hard-coded ratio).
 
-    python tools/ncu_traffic.py gpurun_out/r2_vad.ncu-rep <pairs in the captured launch>
+    python tools/ncu_traffic.py gpurun_out/r2_vad.ncu-rep [pairs in the captured launch]
+
+Without the pair count it is inferred from the launch's DRAM reads (230.4 MB of PCM per 2 h pair);
+in the round-2 capture (`-s 4 -c 1` on `bench.py --pairs 16`) the captured launch is the VAD of the
+bench's host-buffer (e2e) call, 4 pairs.
 """
 import csv
 import io
@@ -32,6 +36,8 @@ def main(path, pairs):
         if "vad_energy_zcr_kernel" not in row[name]:
             continue
         traffic = to_bytes(row[rd], units[rd]) + to_bytes(row[wr], units[wr])
+        if pairs <= 0:
+            pairs = max(1, int(round(to_bytes(row[rd], units[rd]) / 230.4e6)))
         if best is None or traffic > best["dram_bytes_per_launch"]:
             best = {"kernel": "vad_energy_zcr_kernel", "pairs": pairs,
                     "dram_bytes_read": to_bytes(row[rd], units[rd]), "dram_bytes_write": to_bytes(row[wr], units[wr]),
@@ -48,4 +54,4 @@ def main(path, pairs):
 
 
 if __name__ == "__main__":
-    main(sys.argv[1], int(sys.argv[2]))
+    main(sys.argv[1], int(sys.argv[2]) if len(sys.argv) > 2 else 0)
