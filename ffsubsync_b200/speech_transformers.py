@@ -213,6 +213,42 @@ class _BoundedReader:
         return data
 
 
+class _DetectorSink:
+    """Feeds chunks to a detector.  Detectors with the streaming protocol (``stream_begin`` /
+    ``stream_push`` / ``stream_end``: this package's energy detectors, b2_vad_stream_*) only enqueue
+    copy + kernel per chunk, so reading / decoding the next chunk overlaps; any other detector
+    (auditok, fused, third-party factories) is called once per chunk like the reference does (:746)."""
+
+    def __init__(self, detector) -> None:
+        self.detector = detector
+        self.streaming = all(hasattr(detector, a) for a in ("stream_begin", "stream_push", "stream_end"))
+        self.open = False
+        self.pieces: List[np.ndarray] = []
+
+    def feed(self, data: bytes) -> None:
+        if not self.streaming:
+            self.pieces.append(self.detector(np.frombuffer(data, np.uint8)))
+            return
+        if not self.open:
+            self.detector.stream_begin()
+            self.open = True
+        self.detector.stream_push(data)
+
+    def abort(self) -> None:
+        if self.open:
+            self.open = False
+            try:
+                self.detector.stream_end()
+            except Exception:
+                pass
+
+    def finish(self) -> List[np.ndarray]:
+        if self.open:
+            self.open = False
+            self.pieces.append(self.detector.stream_end())
+        return self.pieces
+
+
 class VideoSpeechTransformer(TransformerMixin):
     """PCM -> 100 Hz speech signal.  ``fit`` accepts what the reference accepts (a media path,
     decoded through an ffmpeg subprocess when the binary is available) and, because this layer
@@ -307,62 +343,54 @@ class VideoSpeechTransformer(TransformerMixin):
         proc = subprocess.Popen(args, stdout=subprocess.PIPE, stderr=subprocess.DEVNULL)
         return proc.stdout, None, proc.wait
 
+    # -- chunk loop (speech_transformers.py:680-753) -------------------------------------------------
+    CHUNK_WINDOWS: int = 10000   # 100 s per detector call at the 100 Hz sample rate (:711,741)
+
+    def _chunks(self, readable):
+        """PCM in the reference's read granularity: 10 000 windows of ``2 * frame_rate // sample_rate``
+        bytes each (:710-711,741)."""
+        n = (2 * self.frame_rate // self.sample_rate) * self.CHUNK_WINDOWS
+        while True:
+            data = readable.read(n)
+            if not data:
+                return
+            yield data
+
+    def _report(self, seconds_done: float, seconds_total: Optional[float]) -> None:
+        """Progress protocol (:724-739): the optional callback (its exceptions never break a sync) and
+        the integer-percent lines VLC mode prints."""
+        if self.progress_handler is not None:
+            try:
+                self.progress_handler(ProgressInfo(processed_seconds=seconds_done, total_seconds=seconds_total))
+            except Exception as e:
+                logger.warning("progress_handler raised: %s", e)
+        if self.vlc_mode and seconds_total is not None:
+            print("%d" % int(seconds_done * 100.0 / seconds_total), flush=True)
+
     def fit(self, fname, *_) -> "VideoSpeechTransformer":
-        detector = self._make_detector()
-        stream, total_duration, closer = self._open_source(fname)
-        if self.max_duration_seconds is not None and total_duration is not None:
-            total_duration = min(total_duration, self.max_duration_seconds)
-        media_bstring: List[np.ndarray] = []
-        # detectors that expose the streaming protocol (this package's energy detectors) take the
-        # chunks without a device synchronisation per chunk; anything else is called per chunk
-        streaming = all(hasattr(detector, a) for a in ("stream_begin", "stream_push", "stream_end"))
-        pushed = 0
-        bytes_per_frame = 2
-        bytes_per_window = bytes_per_frame * self.frame_rate // self.sample_rate
-        windows_per_buffer = 10000
-        simple_progress = 0.0
+        sink = _DetectorSink(self._make_detector())
+        readable, total, closer = self._open_source(fname)
+        if total is not None and self.max_duration_seconds is not None:
+            total = min(total, self.max_duration_seconds)
+        done = 0.0
         try:
-            while True:
-                in_bytes = stream.read(bytes_per_window * windows_per_buffer)
-                if not in_bytes:
-                    break
-                newstuff = len(in_bytes) / float(bytes_per_frame) / self.frame_rate
-                if total_duration is not None and simple_progress + newstuff > total_duration:
-                    newstuff = total_duration - simple_progress
-                simple_progress += newstuff
-                if self.progress_handler is not None:
-                    try:
-                        self.progress_handler(ProgressInfo(processed_seconds=simple_progress,
-                                                           total_seconds=total_duration))
-                    except Exception as e:  # a host-supplied callback must never break syncing
-                        logger.warning("progress_handler raised: %s", e)
-                if self.vlc_mode and total_duration is not None:
-                    print("%d" % int(simple_progress * 100.0 / total_duration), flush=True)
-                if streaming:
-                    if pushed == 0:
-                        detector.stream_begin()
-                    detector.stream_push(in_bytes)
-                    pushed += 1
-                else:
-                    media_bstring.append(detector(np.frombuffer(in_bytes, np.uint8)))
+            for data in self._chunks(readable):
+                seconds = len(data) / 2.0 / self.frame_rate
+                done = done + seconds if total is None else min(total, done + seconds)
+                self._report(done, total)
+                sink.feed(data)
         except BaseException:
-            if streaming and pushed:  # close the device-side stream without masking the error
-                try:
-                    detector.stream_end()
-                except Exception:
-                    pass
-                pushed = 0
+            sink.abort()   # close the device-side stream without masking the error
             raise
         finally:
             if closer is not None:
                 closer()
-        if streaming and pushed:
-            media_bstring.append(detector.stream_end())
-        if len(media_bstring) == 0:
+        pieces = sink.finish()
+        if not pieces:
             raise ValueError(
                 "Unable to detect speech. "
                 "Perhaps try specifying a different stream / track, or a different vad.")
-        self.video_speech_results_ = np.concatenate(media_bstring)
+        self.video_speech_results_ = np.concatenate(pieces)
         logger.info("total of speech segments: %s", np.sum(self.video_speech_results_))
         return self
 
