@@ -232,7 +232,7 @@ __device__ __forceinline__ float job_cut(const float2* __restrict__ job_stat, in
   const float2 stat = job_stat[j];
   float cut = stat.x - stat.y;
   approx_only = false;
-  if (winner_only) {
+  if (winner_only) {   // callers pass winner_only = 0 for a job with no_prune set
     const int b0 = (j / K) * K;
     float best_floor = -INFINITY;
     for (int k = 0; k < K; ++k) {
@@ -259,7 +259,7 @@ __global__ void __launch_bounds__(256) big_count_kernel(const SelJob* __restrict
   int cnt = 0;
   if (job.kind == 0 && job.m_lo <= job.m_hi) {
     bool approx;
-    const float cut = job_cut(job_stat, jb.j, K, winner_only, approx);
+    const float cut = job_cut(job_stat, jb.j, K, winner_only && !job.no_prune, approx);
     const float* c = scores + job.score_off;
     const int lo = max(job.m_lo, (int)blockIdx.x * kChunk), hi = min(job.m_hi, (int)(blockIdx.x + 1) * kChunk - 1);
     for (int m = lo + threadIdx.x; m <= hi; m += 256) cnt += c[m] >= cut;
@@ -295,7 +295,7 @@ __global__ void __launch_bounds__(256) big_select_kernel(const SelJob* __restric
     return;
   }
   bool approx_only;
-  const float cut = job_cut(job_stat, jb.j, K, winner_only, approx_only);
+  const float cut = job_cut(job_stat, jb.j, K, winner_only && !job.no_prune, approx_only);
   const float* c = scores + job.score_off;
   if (tid == 0) scount = 0;
   __syncthreads();

@@ -460,7 +460,7 @@ __global__ void __launch_bounds__(256) select_candidates_kernel(
   const float2 stat = job_stat[blockIdx.x];
   float cut = stat.x - stat.y;
   bool approx_only = false;
-  if (winner_only) {
+  if (winner_only && !job.no_prune) {
     const int b0 = (blockIdx.x / K) * K;
     float best_floor = -INFINITY;
     for (int k = 0; k < K; ++k) {
@@ -726,6 +726,11 @@ int b2i_align_launch(b2_ctx* h, const float* d_ref, const int64_t* ref_off, cons
       }
     }
     if (p.any) max_w = std::max(max_w, p.o_max - p.o_min + 1);
+    if (p.any && max_offset_samples != B2_MAX_OFFSET_NONE) {
+      const long long mo = std::max<long long>(-(1LL << 40), std::min<long long>(1LL << 40, max_offset_samples));
+      if (std::max(llabs(p.o_min), llabs(p.o_max)) > mo)
+        for (int k = 0; k < K; ++k) sel[(size_t)b * K + k].no_prune = 1;
+    }
   }
   // offsets per tile: Wt = 1 (mod 32) so that L = P - Wt + 1 is a multiple of 32 (vector loads,
   // whole words of the speech bit mask per block), at most P/2 + 1

@@ -36,6 +36,9 @@ struct SelJob {        // one (pair, ratio)
   int out_index;       // b*K + k
   int kind;            // 0 normal, 1 empty input, 2 everything masked
   int masked_offset;   // offset reported when kind == 2
+  int no_prune;        // 1: some surviving offset of this pair exceeds max_offset_samples in magnitude (the
+                       // negative-slice corners of aligners.py:31-43), so MaxScoreAligner.transform's
+                       // |offset| filter (:160) may drop a ratio's winner - winner-only pruning is off
   long long bits_off;  // >= 0: the subtitle signal is a bit mask (one bit per frame)
   float sub_level;     // value of a frame inside a cue, min(1/ratio, 1) as float32 (bit-mask mode)
 };
