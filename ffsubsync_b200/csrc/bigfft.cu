@@ -429,10 +429,14 @@ int b2i_align_big(b2_ctx* h, const float* d_ref, const float* d_sub, const uint3
     max_tiles = std::max(max_tiles, (g.pairs.size() + 3 * n_sub) * tiles_per);
     max_cnt = std::max(max_cnt, n_sub * ((n + kChunk - 1) / kChunk));
   }
-  MetaArena a;
-  B2_TRY(b2i_meta_begin(h, &a, J * sizeof(SelJob) + 256));
-  const SelJob* d_sel = (const SelJob*)b2i_meta_put(&a, sel.data(), J * sizeof(SelJob));
-  B2_TRY(b2i_meta_commit(&a));
+  // The job table is read by kernels of EVERY group and by the common tail, i.e. long after later
+  // metadata arenas have been committed - outside the reuse contract of the arena ring (a slot may be
+  // recycled 8 arenas later).  It lives in its own workspace; the copy from pageable memory is staged
+  // by the runtime before the call returns.
+  void* d_selv;
+  B2_TRY(b2i_ws(h, b2_ctx::WS_META, J * sizeof(SelJob) + 256, &d_selv));
+  B2_CUDA(h, cudaMemcpyAsync(d_selv, sel.data(), J * sizeof(SelJob), cudaMemcpyHostToDevice, h->stream));
+  const SelJob* d_sel = (const SelJob*)d_selv;
   *d_sel_out = d_sel;
   B2_CUDA(h, cudaMemsetAsync(cb.work_count, 0, sizeof(int), h->stream));
   B2_CUDA(h, cudaMemsetAsync(cb.cand_cnt, 0, J * sizeof(int), h->stream));   // jobs that are not live: no candidates
