@@ -62,6 +62,27 @@ __device__ __forceinline__ Smem carve(unsigned char* raw) {
   return s;
 }
 
+// L2 prefetch of what the NEXT tile of this CTA will load (one 512-thread CTA per SM cannot hide HBM
+// latency with occupancy; the tile's own loads then hit L2).
+__device__ __forceinline__ void l2_prefetch_bulk(const void* p, uint32_t bytes) {   // 16-byte aligned, multiple of 16
+  asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(p), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void l2_prefetch_line(const void* p) {
+  asm volatile("prefetch.global.L2 [%0];" ::"l"(p));
+}
+// rows of an F2 tile (16 x 8 KB)
+__device__ __forceinline__ void prefetch_f2_rows(const float2* base, int q1, int g, int tid) {
+  if (tid < 16) l2_prefetch_bulk(base + ((size_t)f2_row_of_slot(q1, g, tid) << 10), kRow * 8);
+}
+// column group cg of a k1-major [M1][1024] array: M1 segments of cols * 8 bytes
+__device__ __forceinline__ void prefetch_cols(const float2* base, int q1, int cg, int tid) {
+  const int cl = 14 - q1, c0 = cg << cl, seg = 8 << cl;   // bytes per row segment
+  for (int r = tid; r < (1 << q1); r += kThreads) {
+    const char* p = reinterpret_cast<const char*>(base + ((size_t)r << 10) + c0);
+    for (int b = 0; b < seg; b += 128) l2_prefetch_line(p + b);
+  }
+}
+
 __device__ __forceinline__ float block_sum(float v, float* red) {   // all threads call; result on every thread
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
   __syncthreads();
@@ -128,6 +149,12 @@ __global__ void __launch_bounds__(kThreads, 1)
   for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
     const BigXform X = xf[tile / tiles_per];
     const int g = tile % tiles_per;
+    if (tile + (int)gridDim.x < n_tiles) {
+      const int nt = tile + gridDim.x;
+      const BigXform Xn = xf[nt / tiles_per];
+      prefetch_f2_rows(G + Xn.g_off, q1, nt % tiles_per, tid);
+      if (MODE == 1) prefetch_f2_rows(G + Xn.spec_off, q1, nt % tiles_per, tid);
+    }
     f2_load(sm.buf, q1, g, tid, G + X.g_off);
     f2_row_twiddles(sm.row_tw, q1, g, tid);
     __syncthreads();
@@ -165,6 +192,10 @@ __global__ void __launch_bounds__(kThreads, 1)
   for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
     const BigXform X = xf[tile / tiles_per];
     const int cg = tile % tiles_per;
+    if (tile + (int)gridDim.x < n_tiles) {
+      const int nt = tile + gridDim.x;
+      prefetch_cols(G + xf[nt / tiles_per].g_off, Q1, nt % tiles_per, tid);
+    }
     f3_load(sm.buf, Q1, cg, tid, G + X.g_off);
     __syncthreads();
     col_inverse<Q1>(sm.buf, t, tid);

@@ -302,42 +302,54 @@ CORR_HD void retangle_bins(float2 cp, float2 cq, float2 w, float2& zp, float2& z
   zq = make_float2(e.x + tt.y, -e.y + tt.x);
 }
 
-// The pairs of an F2 tile, enumerated so that every bin is visited exactly once:
-//   regular slot pairs (s, 8 + s): element (s, p) <-> (8 + s, 1023 - p), p < 1024
-//   tile 0, s = 0:   row 0     : k2 <-> 1024 - k2 for 0 < k2 < 512, specials k2 = 0 (DC + Nyquist of the
-//                                whole transform) and k2 = 512 (its own partner)
-//                    row M1/2  : k2 <-> 1023 - k2 for k2 < 512
-// `visit(ea, eb, w, kind)`: tile element indices (slot * 1024 + position, NOT swizzled) of the two bins
-// (ea == eb for the self-paired bin), the twiddle w_N^k of the first, kind 0 = regular pair,
-// 1 = DC/Nyquist (ea only), 2 = self-paired bin.
-template <class Visit>
-CORR_HD void f2_for_each_pair(const BigTables& bt, int q1, int g, const float2* row_tw, int tid, Visit visit) {
-  // row_tw[slot] = exp(-i pi k1 / M) for the row in that slot
-#pragma unroll 1
-  for (int it = 0; it < 16; ++it) {
-    const int e = tid + it * kThreads;       // 8192 pair slots: s = e >> 10, p = e & 1023
-    const int s = e >> 10, p = e & 1023;
-    if (g == 0 && s == 0) {
-      // 1024 pair slots shared by the two self-paired rows: p < 512 -> row 0, else row M1/2
-      const int k2 = p & 511;
-      if (p < 512) {
-        if (k2 == 0) {
-          visit(row_pos_of_freq(0), row_pos_of_freq(0), make_float2(1.f, 0.f), 1);
-          const int ih = row_pos_of_freq(512);
-          visit(ih, ih, cmul(row_tw[0], bt.half1024[512]), 2);
-        } else {
-          visit(row_pos_of_freq(k2), row_pos_of_freq(1024 - k2), cmul(row_tw[0], bt.half1024[k2]), 0);
-        }
-      } else {
-        const int pa = row_pos_of_freq(k2);
-        visit(8 * 1024 + pa, 8 * 1024 + 1023 - pa, cmul(row_tw[8], bt.half1024[k2]), 0);
-      }
+// The pairs of an F2 tile, enumerated so that every bin is visited exactly once: pair slot
+// e = s * 1024 + p, s < 8, p < 1024 (16 slots per thread) plus ONE extra visit in tile 0:
+//   regular slot pairs (s, 8 + s): element (s, p) <-> (8 + s, 1023 - p)
+//   tile 0, s = 0:   row 0     : k2 <-> 1024 - k2 for 0 < k2 < 512 (p = k2), k2 = 0 = DC + Nyquist of
+//                                the whole transform (p = 0); its own partner k2 = 512 is the extra visit
+//                    row M1/2  : k2 <-> 1023 - k2 for k2 < 512 (p = 512 + k2)
+// ea, eb: tile element indices (slot * 1024 + position, NOT swizzled) of the two bins (ea == eb for the
+// self-paired bin); w = w_N^k of the first; kind 0 = regular pair, 1 = DC/Nyquist (ea only),
+// 2 = self-paired bin.
+struct PairGeo {
+  int ea, eb, kind;
+  float2 w;
+};
+CORR_HD PairGeo f2_pair(const BigTables& bt, int g, const float2* row_tw, int e) {
+  const int s = e >> 10, p = e & 1023;
+  PairGeo r;
+  r.kind = 0;
+  if (g == 0 && s == 0) {
+    const int k2 = p & 511;
+    if (p >= 512) {
+      const int pa = row_pos_of_freq(k2);
+      r.ea = 8 * 1024 + pa;
+      r.eb = 8 * 1024 + 1023 - pa;
+      r.w = cmul(row_tw[8], bt.half1024[k2]);
+    } else if (k2 == 0) {
+      r.ea = r.eb = row_pos_of_freq(0);
+      r.w = make_float2(1.f, 0.f);
+      r.kind = 1;
     } else {
-      const int k2 = row_freq_of_pos(p);
-      visit(s * 1024 + p, (8 + s) * 1024 + 1023 - p, cmul(row_tw[s], bt.half1024[k2]), 0);
+      r.ea = row_pos_of_freq(k2);
+      r.eb = row_pos_of_freq(1024 - k2);
+      r.w = cmul(row_tw[0], bt.half1024[k2]);
     }
+  } else {
+    r.ea = s * 1024 + p;
+    r.eb = (8 + s) * 1024 + 1023 - p;
+    r.w = cmul(row_tw[s], bt.half1024[row_freq_of_pos(p)]);
   }
+  return r;
 }
+CORR_HD PairGeo f2_extra_pair(const BigTables& bt, const float2* row_tw) {   // tile 0 only: bin k = M/2
+  PairGeo r;
+  r.ea = r.eb = row_pos_of_freq(512);
+  r.w = cmul(row_tw[0], bt.half1024[512]);
+  r.kind = 2;
+  return r;
+}
+constexpr int kPairSlotsPerThread = 8 * 1024 / kThreads;   // 16
 
 // scale of the real outputs: unnormalised transforms (M) and factors 2 (A), 2 (B), 2 (retangle)
 CORR_HD float out_scale(int q1) { return 1.0f / (8.0f * (float)(1 << (q1 + 10))); }
@@ -371,14 +383,25 @@ CORR_HD float2 source_pair(const BigSource& s, int n) {   // samples 2 n, 2 n + 
 
 // F1 load: tile cg = columns [cg * cols, (cg + 1) * cols) of the [M1][1024] array z[n] = x[2n] + i x[2n+1].
 // Returns the thread's partial sum of squares.
+// (global loads are issued in batches of kLoadBatch per thread before their results are used: one
+// 512-thread CTA per SM has to cover the HBM / L2 latency with loads in flight, not with warps)
+constexpr int kLoadBatch = 8;
 CORR_HD float f1_load(float2* buf, const BigSource& src, int q1, int cg, int tid) {
   const int cl = 14 - q1, c0 = cg << cl;
   float ss = 0.f;
-  for (int e = tid; e < kM; e += kThreads) {
-    const int n1 = e >> cl, c = e & ((1 << cl) - 1);
-    const float2 v = source_pair(src, (n1 << 10) + c0 + c);
-    ss += v.x * v.x + v.y * v.y;
-    buf[swz(e)] = v;
+#pragma unroll 1
+  for (int e0 = tid; e0 < kM; e0 += kLoadBatch * kThreads) {
+    float2 v[kLoadBatch];
+#pragma unroll
+    for (int i = 0; i < kLoadBatch; ++i) {
+      const int e = e0 + i * kThreads;
+      v[i] = source_pair(src, ((e >> cl) << 10) + c0 + (e & ((1 << cl) - 1)));
+    }
+#pragma unroll
+    for (int i = 0; i < kLoadBatch; ++i) {
+      ss += v[i].x * v[i].x + v[i].y * v[i].y;
+      buf[swz(e0 + i * kThreads)] = v[i];
+    }
   }
   return ss;
 }
@@ -394,8 +417,17 @@ CORR_HD void f1_store(const float2* buf, const BigTables& bt, int q1, int cg, in
 
 // F2 load / store of the 16 rows of tile g (slot order, see f2_row_of_slot).
 CORR_HD void f2_load(float2* buf, int q1, int g, int tid, const float2* src) {
-  for (int e = tid; e < kM; e += kThreads)
-    buf[swz(e)] = CORR_LDG(src + ((size_t)f2_row_of_slot(q1, g, e >> 10) << 10) + (e & 1023));
+#pragma unroll 1
+  for (int e0 = tid; e0 < kM; e0 += kLoadBatch * kThreads) {
+    float2 v[kLoadBatch];
+#pragma unroll
+    for (int i = 0; i < kLoadBatch; ++i) {
+      const int e = e0 + i * kThreads;
+      v[i] = CORR_LDG(src + ((size_t)f2_row_of_slot(q1, g, e >> 10) << 10) + (e & 1023));
+    }
+#pragma unroll
+    for (int i = 0; i < kLoadBatch; ++i) buf[swz(e0 + i * kThreads)] = v[i];
+  }
 }
 CORR_HD void f2_store(const float2* buf, int q1, int g, int tid, float2* dst) {
   for (int e = tid; e < kM; e += kThreads)
@@ -410,44 +442,64 @@ CORR_HD void f2_row_twiddles(float2* row_tw, int q1, int g, int tid) {
   }
 }
 // Reference: rows (already transformed, position order) -> packed real spectrum 2 B[k], in place.
+CORR_HD void untangle_visit(float2* buf, const PairGeo& pg) {
+  const int ia = swz(pg.ea), ib = swz(pg.eb);
+  const float2 zp = buf[ia], zq = buf[ib];
+  if (pg.kind == 1) {
+    buf[ia] = make_float2(2.f * (zp.x + zp.y), 2.f * (zp.x - zp.y));   // DC, Nyquist
+    return;
+  }
+  float2 hp, hq;
+  untangle_bins(zp, zq, pg.w, hp, hq);
+  buf[ia] = hp;
+  if (pg.kind == 0) buf[ib] = hq;
+}
 CORR_HD void f2_untangle_inplace(float2* buf, const BigTables& bt, int q1, int g, const float2* row_tw, int tid) {
-  f2_for_each_pair(bt, q1, g, row_tw, tid, [&](int ea, int eb, float2 w, int kind) {
-    const int ia = swz(ea), ib = swz(eb);
-    const float2 zp = buf[ia], zq = buf[ib];
-    if (kind == 1) {
-      buf[ia] = make_float2(2.f * (zp.x + zp.y), 2.f * (zp.x - zp.y));   // DC, Nyquist
-      return;
-    }
-    float2 hp, hq;
-    untangle_bins(zp, zq, w, hp, hq);
-    buf[ia] = hp;
-    if (kind == 0) buf[ib] = hq;
-  });
+#pragma unroll 1
+  for (int it = 0; it < kPairSlotsPerThread; ++it) untangle_visit(buf, f2_pair(bt, g, row_tw, tid + it * kThreads));
+  if (g == 0 && tid == 0) untangle_visit(buf, f2_extra_pair(bt, row_tw));
 }
 // Subtitles: rows (transformed) -> conj(2 A) * (2 B) -> packed for the inverse transform, in place.
 // spec = the stored reference spectrum of the same transform geometry (tile layout [k1][position]).
+CORR_HD size_t spec_index(int q1, int g, int e) { return ((size_t)f2_row_of_slot(q1, g, e >> 10) << 10) + (e & 1023); }
+CORR_HD void product_visit(float2* buf, const PairGeo& pg, float2 bp, float2 bq) {
+  const int ia = swz(pg.ea), ib = swz(pg.eb);
+  const float2 zp = buf[ia], zq = buf[ib];
+  if (pg.kind == 1) {
+    const float c0 = 2.f * (zp.x + zp.y) * bp.x, cm = 2.f * (zp.x - zp.y) * bp.y;
+    buf[ia] = make_float2(c0 + cm, c0 - cm);
+    return;
+  }
+  float2 hp, hq;
+  untangle_bins(zp, zq, pg.w, hp, hq);
+  const float2 cp = cmul_conj_a(hp, bp);
+  const float2 cq = pg.kind == 0 ? cmul_conj_a(hq, bq) : cp;
+  float2 np, nq;
+  retangle_bins(cp, cq, pg.w, np, nq);
+  buf[ia] = np;
+  if (pg.kind == 0) buf[ib] = nq;
+}
 CORR_HD void f2_product_inplace(float2* buf, const BigTables& bt, int q1, int g, const float2* row_tw, int tid,
                                 const float2* spec) {
-  f2_for_each_pair(bt, q1, g, row_tw, tid, [&](int ea, int eb, float2 w, int kind) {
-    const int ia = swz(ea), ib = swz(eb);
-    const float2 zp = buf[ia], zq = buf[ib];
-    const float2 bp = CORR_LDG(spec + ((size_t)f2_row_of_slot(q1, g, ea >> 10) << 10) + (ea & 1023));
-    if (kind == 1) {
-      const float c0 = 2.f * (zp.x + zp.y) * bp.x, cm = 2.f * (zp.x - zp.y) * bp.y;
-      buf[ia] = make_float2(c0 + cm, c0 - cm);
-      return;
+  constexpr int kB = 4;   // pairs per batch: 8 spectrum loads in flight per thread
+#pragma unroll 1
+  for (int it0 = 0; it0 < kPairSlotsPerThread; it0 += kB) {
+    PairGeo pg[kB];
+    float2 bp[kB], bq[kB];
+#pragma unroll
+    for (int i = 0; i < kB; ++i) {
+      pg[i] = f2_pair(bt, g, row_tw, tid + (it0 + i) * kThreads);
+      bp[i] = CORR_LDG(spec + spec_index(q1, g, pg[i].ea));
+      bq[i] = CORR_LDG(spec + spec_index(q1, g, pg[i].eb));
     }
-    float2 hp, hq;
-    untangle_bins(zp, zq, w, hp, hq);
-    const float2 cp = cmul_conj_a(hp, bp);
-    float2 cq = cp;
-    if (kind == 0)
-      cq = cmul_conj_a(hq, CORR_LDG(spec + ((size_t)f2_row_of_slot(q1, g, eb >> 10) << 10) + (eb & 1023)));
-    float2 np, nq;
-    retangle_bins(cp, cq, w, np, nq);
-    buf[ia] = np;
-    if (kind == 0) buf[ib] = nq;
-  });
+#pragma unroll
+    for (int i = 0; i < kB; ++i) product_visit(buf, pg[i], bp[i], bq[i]);
+  }
+  if (g == 0 && tid == 0) {
+    const PairGeo pg = f2_extra_pair(bt, row_tw);
+    const float2 b = CORR_LDG(spec + spec_index(q1, g, pg.ea));
+    product_visit(buf, pg, b, b);
+  }
 }
 // F2 (subtitles) store after the inverse row transform: conjugate four-step twiddle.
 CORR_HD void f2_store_twiddled(const float2* buf, const BigTables& bt, int q1, int g, int tid, float2* dst) {
@@ -462,9 +514,16 @@ CORR_HD void f2_store_twiddled(const float2* buf, const BigTables& bt, int q1, i
 // F3 load: columns of the k1-major array into row positions (digit-reversed for the inverse passes).
 CORR_HD void f3_load(float2* buf, int q1, int cg, int tid, const float2* g) {
   const int cl = 14 - q1, c0 = cg << cl;
-  for (int e = tid; e < kM; e += kThreads) {
-    const int k1 = col_freq_of_pos(q1, e >> cl);
-    buf[swz(e)] = CORR_LDG(g + ((size_t)k1 << 10) + c0 + (e & ((1 << cl) - 1)));
+#pragma unroll 1
+  for (int e0 = tid; e0 < kM; e0 += kLoadBatch * kThreads) {
+    float2 v[kLoadBatch];
+#pragma unroll
+    for (int i = 0; i < kLoadBatch; ++i) {
+      const int e = e0 + i * kThreads;
+      v[i] = CORR_LDG(g + ((size_t)col_freq_of_pos(q1, e >> cl) << 10) + c0 + (e & ((1 << cl) - 1)));
+    }
+#pragma unroll
+    for (int i = 0; i < kLoadBatch; ++i) buf[swz(e0 + i * kThreads)] = v[i];
   }
 }
 // F3 store: c[2n], c[2n+1] = re, im of z[n]; score index m = (lag + S) mod N (offset o = m - S).
