@@ -1056,3 +1056,57 @@ def test_ffmpeg_and_ffprobe_subprocess_branches(handle, tmp_path, monkeypatch):
     assert np.array_equal(sparse, raw) and sparse.sum() > 0
     with pytest.raises(ValueError, match="no ffmpeg binary"):
         VideoSpeechTransformer("energy_zcr", 100, 16000, 0.0, ffmpeg_path=str(tmp_path / "nowhere")).fit("movie.mkv")
+
+
+# ================================================= adversarial signal families (round-off bound, ties)
+
+def _adv_family(name, n, rng, level=1.0):
+    if name == "random":
+        return (rng.rand(n) > rng.uniform(0.2, 0.8)).astype(np.float32) * np.float32(level)
+    if name == "ones":
+        return np.full(n, level, np.float32)
+    if name == "period2":
+        return (np.arange(n) % 2).astype(np.float32) * np.float32(level)
+    if name == "period_block":
+        return ((np.arange(n) // 10368) % 2).astype(np.float32) * np.float32(level)
+    if name == "sparse":
+        x = np.zeros(n, np.float32)
+        for s in rng.randint(0, max(1, n - 6000), 6):
+            x[s:s + 6000] = (rng.rand(len(x[s:s + 6000])) > 0.5) * np.float32(level)
+        return x
+    if name == "wide":
+        return (10.0 ** rng.uniform(-3, 3, n) * rng.choice([0.0, 1.0], n)).astype(np.float32)
+    raise ValueError(name)
+
+
+@pytest.mark.parametrize("mos", [6000, None])
+def test_adversarial_families_offsets_are_exact_maxima(handle, mos):
+    """Constant, periodic, sparse and wide-dynamic-range signals (large means, flat or periodic
+    correlation landscapes, many exact ties) through both correlation paths: the returned offset must
+    attain the maximum of the EXACT scores over the surviving window (the reference breaks exact ties
+    by its float64 round-off, so only the score and tie-membership are comparable), unless the kernel
+    flagged more tied candidates than its re-score budget."""
+    from ffsubsync_b200 import _native
+    fams = ["random", "ones", "period2", "period_block", "sparse", "wide"]
+    rng = np.random.RandomState(77)
+    refs, subs, meta = [], [], []
+    for fr in fams:
+        for fs in fams:
+            refs.append(_adv_family(fr, 70000, rng))
+            subs.append(_adv_family(fs, 66000, rng, 0.96))
+            meta.append((fr, fs))
+    B = len(refs)
+    ref_off = np.arange(B + 1, dtype=np.int64) * 70000
+    sub_off = np.arange(B + 1, dtype=np.int64) * 66000
+    score, off, st = handle.align_batch(np.concatenate(refs), ref_off, np.concatenate(subs), sub_off, B, 1, mos)
+    n_flagged = 0
+    for b in range(B):
+        if st[b] & _native.ALIGN_CAND_OVERFLOW:
+            n_flagged += 1
+            continue
+        ws, wo = ao.fft_align(refs[b], subs[b], mos)
+        mine = ao.exact_score(refs[b], subs[b], int(off[b]))
+        tol = 1e-9 * max(abs(ws), 1.0) + 1e-6 * float(np.abs(2 * subs[b] - 1).max() * np.abs(2 * refs[b] - 1).max())
+        assert abs(score[b] - mine) <= 1e-9 * max(abs(mine), 1.0) + 1e-9, (meta[b], score[b], mine)
+        assert mine >= ws - tol and _score_ok(score[b], ws), (meta[b], mos, off[b], wo, mine, ws)
+    assert n_flagged <= 12, n_flagged   # constant / periodic against each other: plateaus of exact ties
