@@ -135,6 +135,18 @@ class ClockSampler:
 
 # ------------------------------------------------------------------------------------ GPU arm
 
+def workload_config(world, B, K):
+    """The `config` object both arms print (same keys and values: the reference arm times a bounded
+    sample of THIS workload, see its cpu_baseline.sample)."""
+    name = ("BASELINE configs[3]: 4096 two-hour pairs sharded over 8 GPUs (512 per GPU)"
+            if (world == 8 and B == 512) else
+            "BASELINE configs[2]: batch of 256 two-hour pairs per GPU" if B == 256 else
+            "batch of %d two-hour pairs per GPU (BASELINE configs[2] workload at another batch size)" % B)
+    return {"workload": name + ", with the VAD of configs[1]: 16 kHz mono s16le PCM -> energy/ZCR "
+                               "VAD -> MaxScoreAligner over K ratios, max_offset_seconds=60",
+            "pairs_per_gpu": B, "ratios": K, "signal_frames": 720000, "pcm_samples_per_pair": 115200000}
+
+
 def default_pairs(world):
     """BASELINE configs[2]: 256 two-hour pairs on one GPU; configs[3]: 4096 pairs over 8 GPUs =
     512 per GPU.  (2 and 4 GPUs keep 256 per GPU.)  B2_BENCH_PAIRS / --pairs override."""
@@ -459,23 +471,16 @@ def run_gpu(args):
 
     if rank == 0:
         total_pairs = B * world * steps
-        cfg_name = ("BASELINE configs[3]: 4096 two-hour pairs sharded over 8 GPUs (512 per GPU)"
-                    if (world == 8 and B == 512) else
-                    "BASELINE configs[2]: batch of 256 two-hour pairs per GPU" if B == 256 else
-                    "batch of %d two-hour pairs per GPU (BASELINE configs[2] workload at another batch size)" % B)
         line = {
             "metric": METRIC, "value": total_pairs / (elapsed_ms * 1e-3), "unit": UNIT, "n_gpus": world,
             "steps": steps, "warmup": args.warmup, "ms_per_step": elapsed_ms / steps,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "int64 VAD; f32 FFT nomination + f64 exact re-score", "data": "synthetic",
-            "config": {"workload": cfg_name + ", with the VAD of configs[1]: 16 kHz mono s16le PCM -> energy/ZCR "
-                                   "VAD -> MaxScoreAligner over K ratios, max_offset_seconds=60",
-                       "pairs_per_gpu": B, "ratios": K,
-                       "signal_frames": 720000, "pcm_samples_per_pair": 115200000,
-                       "l2_policy": "inputs (%.1f GB PCM per GPU) are far larger than the 126 MB L2"
-                                    % (B * 0.2304), "parallelism": "pairs block-sharded, dp%d" % world,
-                       "exchange": ("NCCL all_gather_into_tensor of 24 B/pair per step on a side stream "
-                                    "(event-ordered after the step's results)") if gather else None},
+            "config": dict(workload_config(world, B, K),
+                           l2_policy="inputs (%.1f GB PCM per GPU) are far larger than the 126 MB L2" % (B * 0.2304),
+                           parallelism="pairs block-sharded, dp%d" % world,
+                           exchange=("NCCL all_gather_into_tensor of 24 B/pair per step on a side stream "
+                                     "(event-ordered after the step's results)") if gather else None),
             "verified_offsets": ok, "verified_vs_oracle": oracle_check, "gpu_launches": int(launches),
             "clocks": clocks, "per_rank": per_rank, "stages_ms": stages,
             "timed_region_s": elapsed_ms * 1e-3,
@@ -582,6 +587,7 @@ def cpu_baseline_sample(K, ratios, budget_pairs=None):
 
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
     if rank != 0:
         return
     from ffsubsync_b200.synth import BENCH_RATIOS
@@ -605,9 +611,11 @@ def run_reference(args):
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "int64 VAD; complex128 FFT",
         "data": "synthetic",
-        "config": {"workload": "same as the GPU arm: 2 h pairs, 16 kHz PCM -> energy/ZCR detector (numpy "
-                               "restatement) -> FFTAligner (numpy complex128, aligners.py:50-80) over K ratios, "
-                               "max_offset_seconds=60", "pairs_per_step": per_step, "ratios": K},
+        "config": dict(workload_config(world, args.pairs if args.pairs else default_pairs(world), K),
+                       implementation="the reference's algorithm on the host: energy/ZCR detector (numpy restatement, "
+                                      "100 s chunks) -> SubtitleScaler + rasteriser per ratio -> FFTAligner (numpy "
+                                      "complex128, aligners.py:50-80) -> MaxScoreAligner",
+                       sample_pairs_per_step=per_step),
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": used, "host_cores": cores,
                          "cores_source": quota_src, "kind": "port",
                          "sample": "%d two-hour pairs per step, one per worker process" % per_step},
