@@ -46,19 +46,21 @@ struct BigJob {          // one (pair, ratio) of the group
 };
 
 constexpr int kChunk = 32768;   // offsets per counting CTA
-constexpr size_t kBigSmemBytes = kSmemBytes + 1024 * 8 + ((size_t)8 << kMaxQ1) + 16 * 8 + 64;
+constexpr int kFineCap = (1 << kMaxQ1) + (1 << (kMaxQ1 - 4)) + (1 << (kMaxQ1 - 8)) + 4;   // skewed size
+constexpr size_t kBigSmemBytes = kSmemBytes + 1024 * 8 + (size_t)kSkew1024 * 8 + (size_t)kFineCap * 8 + 16 * 8 + 64;
 
 struct Smem {
-  float2 *buf, *tw1024, *fine32, *half1024, *fine, *row_tw;
+  float2 *buf, *tw1024, *fine32, *half_pos, *coarse, *fine, *row_tw;
 };
 __device__ __forceinline__ Smem carve(unsigned char* raw) {
   Smem s;
   s.buf = reinterpret_cast<float2*>(raw);
   s.tw1024 = s.buf + kM;
   s.fine32 = s.tw1024 + 1024;
-  s.half1024 = s.fine32 + 32;
-  s.fine = s.half1024 + 1024;
-  s.row_tw = s.fine + (1 << kMaxQ1);
+  s.half_pos = s.fine32 + 32;
+  s.coarse = s.half_pos + 1024;
+  s.fine = s.coarse + kSkew1024;
+  s.row_tw = s.fine + kFineCap;
   return s;
 }
 
@@ -113,10 +115,10 @@ __global__ void __launch_bounds__(kThreads, 1)
   const Smem sm = carve(smem_raw);
   const int tid = threadIdx.x;
   init_tables(sm.tw1024, sm.fine32, tid);
-  init_big_tables(sm.half1024, sm.fine, Q1, tid);
+  init_big_tables(sm.half_pos, sm.coarse, sm.fine, Q1, tid);
   __syncthreads();
   const Tables t{sm.tw1024, sm.fine32};
-  const BigTables bt{sm.tw1024, sm.fine32, sm.half1024, sm.fine};
+  const BigTables bt{sm.tw1024, sm.fine32, sm.half_pos, sm.coarse, sm.fine};
   constexpr int tiles_per = (1 << Q1) / 16;
   for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
     const BigXform X = xf[tile / tiles_per];
@@ -141,10 +143,10 @@ __global__ void __launch_bounds__(kThreads, 1)
   const Smem sm = carve(smem_raw);
   const int tid = threadIdx.x;
   init_tables(sm.tw1024, sm.fine32, tid);
-  init_big_tables(sm.half1024, sm.fine, q1, tid);
+  init_big_tables(sm.half_pos, sm.coarse, sm.fine, q1, tid);
   __syncthreads();
   const Tables t{sm.tw1024, sm.fine32};
-  const BigTables bt{sm.tw1024, sm.fine32, sm.half1024, sm.fine};
+  const BigTables bt{sm.tw1024, sm.fine32, sm.half_pos, sm.coarse, sm.fine};
   const int tiles_per = (1 << q1) / 16;
   for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
     const BigXform X = xf[tile / tiles_per];

@@ -248,31 +248,41 @@ CORR_HD int row_freq_of_pos(int p) { return ((p >> 6) & 15) | (((p >> 2) & 15) <
 CORR_HD int row_pos_of_freq(int f) { return ((f & 15) << 6) | (((f >> 4) & 15) << 2) | (f >> 8); }
 
 // ---- tables -------------------------------------------------------------------------------------
-// half1024[t] = exp(-i pi t / 1024) (untangle: the k2 part of w_N^k);  fine[t] = exp(-2 pi i t / M),
-// t < M1 (four-step twiddle: w_M^x = tw1024[x >> q1] * fine[x & (M1 - 1)]).
+// half_pos[p] = exp(-i pi k2 / 1024), k2 = row_freq_of_pos(p): the k2 part of the untangle twiddle
+//   w_N^k, stored in POSITION order (consecutive lanes read consecutive entries; in frequency order
+//   the digit-reversed k2 of 32 consecutive positions all fall into one bank);
+// coarse[skew(t)] = exp(-2 pi i t / 1024), fine[skew(t)] = exp(-2 pi i t / M), t < M1: four-step
+//   twiddle w_M^x = coarse[x >> q1] * fine[x & (M1 - 1)].  x = n2 * k1 runs over a warp with stride k1,
+//   often a multiple of a power of two: the skew t + t/16 + t/256 spreads such strides over the banks.
+CORR_HD int skew(int t) { return t + (t >> 4) + (t >> 8); }
+constexpr int kSkew1024 = 1024 + 64 + 4;
 struct BigTables {
   const float2* tw1024;
   const float2* fine32;
-  const float2* half1024;
+  const float2* half_pos;
+  const float2* coarse;
   const float2* fine;
 };
-CORR_HD void init_big_tables(float2* half1024, float2* fine, int q1, int tid) {
+CORR_HD int row_freq_of_pos(int p);
+CORR_HD void init_big_tables(float2* half_pos, float2* coarse, float2* fine, int q1, int tid) {
   for (int t = tid; t < 1024; t += kThreads) {
     float s, c;
-    sincospif(-(float)t * (1.0f / 1024.0f), &s, &c);
-    half1024[t] = make_float2(c, s);
+    sincospif(-(float)row_freq_of_pos(t) * (1.0f / 1024.0f), &s, &c);
+    half_pos[t] = make_float2(c, s);
+    sincospif(-(float)t * (1.0f / 512.0f), &s, &c);
+    coarse[skew(t)] = make_float2(c, s);
   }
   const int m1 = 1 << q1;
   const float inv_half_m = 2.0f / (float)(m1 << 10);   // exp(-2 pi i t / M) = sincospi(-2 t / M)
   for (int t = tid; t < m1; t += kThreads) {
     float s, c;
     sincospif(-(float)t * inv_half_m, &s, &c);
-    fine[t] = make_float2(c, s);
+    fine[skew(t)] = make_float2(c, s);
   }
 }
 // w_M^x, x < M = 2^(q1 + 10)
 CORR_HD float2 step_twiddle(const BigTables& bt, int q1, int x) {
-  return cmul(bt.tw1024[x >> q1], bt.fine[x & ((1 << q1) - 1)]);
+  return cmul(bt.coarse[skew(x >> q1)], bt.fine[skew(x & ((1 << q1) - 1))]);
 }
 
 // ---- tile geometry --------------------------------------------------------------------------------
@@ -325,7 +335,7 @@ CORR_HD PairGeo f2_pair(const BigTables& bt, int g, const float2* row_tw, int e)
       const int pa = row_pos_of_freq(k2);
       r.ea = 8 * 1024 + pa;
       r.eb = 8 * 1024 + 1023 - pa;
-      r.w = cmul(row_tw[8], bt.half1024[k2]);
+      r.w = cmul(row_tw[8], bt.half_pos[pa]);
     } else if (k2 == 0) {
       r.ea = r.eb = row_pos_of_freq(0);
       r.w = make_float2(1.f, 0.f);
@@ -333,19 +343,19 @@ CORR_HD PairGeo f2_pair(const BigTables& bt, int g, const float2* row_tw, int e)
     } else {
       r.ea = row_pos_of_freq(k2);
       r.eb = row_pos_of_freq(1024 - k2);
-      r.w = cmul(row_tw[0], bt.half1024[k2]);
+      r.w = cmul(row_tw[0], bt.half_pos[r.ea]);
     }
   } else {
     r.ea = s * 1024 + p;
     r.eb = (8 + s) * 1024 + 1023 - p;
-    r.w = cmul(row_tw[s], bt.half1024[row_freq_of_pos(p)]);
+    r.w = cmul(row_tw[s], bt.half_pos[p]);
   }
   return r;
 }
 CORR_HD PairGeo f2_extra_pair(const BigTables& bt, const float2* row_tw) {   // tile 0 only: bin k = M/2
   PairGeo r;
   r.ea = r.eb = row_pos_of_freq(512);
-  r.w = cmul(row_tw[0], bt.half1024[512]);
+  r.w = cmul(row_tw[0], bt.half_pos[r.ea]);
   r.kind = 2;
   return r;
 }
@@ -365,37 +375,56 @@ struct BigSource {
   int len;
   float hi;
 };
-CORR_HD float2 source_pair(const BigSource& s, int n) {   // samples 2 n, 2 n + 1
-  const int t0 = 2 * n;
-  float2 v = make_float2(0.f, 0.f);
-  if (s.bits) {
-    if (t0 < s.len) {
-      const uint32_t w = CORR_LDG(s.bits + (t0 >> 5)) >> (t0 & 31);   // t0 even: both bits in one word
-      v.x = (w & 1u) ? s.hi : -1.f;
-      if (t0 + 1 < s.len) v.y = (w & 2u) ? s.hi : -1.f;
-    }
-  } else {
-    if (t0 < s.len) v.x = 2.f * CORR_LDG(s.f + t0) - 1.f;
-    if (t0 + 1 < s.len) v.y = 2.f * CORR_LDG(s.f + t0 + 1) - 1.f;
-  }
-  return v;
-}
-
 // F1 load: tile cg = columns [cg * cols, (cg + 1) * cols) of the [M1][1024] array z[n] = x[2n] + i x[2n+1].
-// Returns the thread's partial sum of squares.
-// (global loads are issued in batches of kLoadBatch per thread before their results are used: one
-// 512-thread CTA per SM has to cover the HBM / L2 latency with loads in flight, not with warps)
+// Returns the thread's partial sum of squares.  Global loads are issued in batches of kLoadBatch per
+// thread with clamped (always valid) addresses and masked afterwards, so that the loads of a batch are
+// in flight together (one 512-thread CTA per SM covers the latency with loads in flight, not with
+// warps); batches that lie entirely in the zero padding issue no loads.
 constexpr int kLoadBatch = 8;
 CORR_HD float f1_load(float2* buf, const BigSource& src, int q1, int cg, int tid) {
-  const int cl = 14 - q1, c0 = cg << cl;
+  const int cl = 14 - q1, c0 = cg << cl, cmask = (1 << cl) - 1;
+  const int last = src.len - 1;   // len >= 1 (empty signals never reach the transforms)
   float ss = 0.f;
 #pragma unroll 1
   for (int e0 = tid; e0 < kM; e0 += kLoadBatch * kThreads) {
-    float2 v[kLoadBatch];
+    if (2 * (((e0 >> cl) << 10) + c0 + (e0 & cmask)) >= src.len) {   // n grows with e: the rest is padding
 #pragma unroll
-    for (int i = 0; i < kLoadBatch; ++i) {
-      const int e = e0 + i * kThreads;
-      v[i] = source_pair(src, ((e >> cl) << 10) + c0 + (e & ((1 << cl) - 1)));
+      for (int i = 0; i < kLoadBatch; ++i) buf[swz(e0 + i * kThreads)] = make_float2(0.f, 0.f);
+      continue;
+    }
+    float2 v[kLoadBatch];
+    if (src.bits) {
+      uint32_t w[kLoadBatch];
+#pragma unroll
+      for (int i = 0; i < kLoadBatch; ++i) {
+        const int e = e0 + i * kThreads;
+        const int t0 = 2 * (((e >> cl) << 10) + c0 + (e & cmask));
+        w[i] = CORR_LDG(src.bits + ((t0 < last ? t0 : last) >> 5));
+      }
+#pragma unroll
+      for (int i = 0; i < kLoadBatch; ++i) {
+        const int e = e0 + i * kThreads;
+        const int t0 = 2 * (((e >> cl) << 10) + c0 + (e & cmask));
+        const uint32_t m = w[i] >> (t0 & 31);   // t0 even: both bits in one word
+        v[i].x = t0 < src.len ? ((m & 1u) ? src.hi : -1.f) : 0.f;
+        v[i].y = t0 + 1 < src.len ? ((m & 2u) ? src.hi : -1.f) : 0.f;
+      }
+    } else {
+      float a[kLoadBatch], b[kLoadBatch];
+#pragma unroll
+      for (int i = 0; i < kLoadBatch; ++i) {
+        const int e = e0 + i * kThreads;
+        const int t0 = 2 * (((e >> cl) << 10) + c0 + (e & cmask));
+        a[i] = CORR_LDG(src.f + (t0 < last ? t0 : last));
+        b[i] = CORR_LDG(src.f + (t0 + 1 < last ? t0 + 1 : last));
+      }
+#pragma unroll
+      for (int i = 0; i < kLoadBatch; ++i) {
+        const int e = e0 + i * kThreads;
+        const int t0 = 2 * (((e >> cl) << 10) + c0 + (e & cmask));
+        v[i].x = t0 < src.len ? 2.f * a[i] - 1.f : 0.f;
+        v[i].y = t0 + 1 < src.len ? 2.f * b[i] - 1.f : 0.f;
+      }
     }
 #pragma unroll
     for (int i = 0; i < kLoadBatch; ++i) {

@@ -63,11 +63,11 @@ int main(int argc, char** argv) {
   const int M = 1 << (q1 + 10), N = 2 * M, tiles = (1 << q1) / 16;
   if (R + S > N) return 5;
 
-  std::vector<float2> buf(kM), tw(1024), fine32(32), half(1024), finem(1 << q1), row_tw(16);
+  std::vector<float2> buf(kM), tw(1024), fine32(32), half(1024), coarse(kSkew1024), finem(skew(1 << q1) + 4), row_tw(16);
   for (int tid = 0; tid < kThreads; ++tid) init_tables(tw.data(), fine32.data(), tid);
-  for (int tid = 0; tid < kThreads; ++tid) init_big_tables(half.data(), finem.data(), q1, tid);
+  for (int tid = 0; tid < kThreads; ++tid) init_big_tables(half.data(), coarse.data(), finem.data(), q1, tid);
   const Tables t{tw.data(), fine32.data()};
-  const BigTables bt{tw.data(), fine32.data(), half.data(), finem.data()};
+  const BigTables bt{tw.data(), fine32.data(), half.data(), coarse.data(), finem.data()};
 
   float level = 0.f;
   for (float v : sub) level = v > level ? v : level;

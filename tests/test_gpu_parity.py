@@ -1099,14 +1099,19 @@ def test_adversarial_families_offsets_are_exact_maxima(handle, mos):
     ref_off = np.arange(B + 1, dtype=np.int64) * 70000
     sub_off = np.arange(B + 1, dtype=np.int64) * 66000
     score, off, st = handle.align_batch(np.concatenate(refs), ref_off, np.concatenate(subs), sub_off, B, 1, mos)
-    n_flagged = 0
+    n_flagged, problems = 0, []
     for b in range(B):
-        if st[b] & _native.ALIGN_CAND_OVERFLOW:
-            n_flagged += 1
-            continue
         ws, wo = ao.fft_align(refs[b], subs[b], mos)
         mine = ao.exact_score(refs[b], subs[b], int(off[b]))
         tol = 1e-9 * max(abs(ws), 1.0) + 1e-6 * float(np.abs(2 * subs[b] - 1).max() * np.abs(2 * refs[b] - 1).max())
-        assert abs(score[b] - mine) <= 1e-9 * max(abs(mine), 1.0) + 1e-9, (meta[b], score[b], mine)
-        assert mine >= ws - tol and _score_ok(score[b], ws), (meta[b], mos, off[b], wo, mine, ws)
-    assert n_flagged <= 12, n_flagged   # constant / periodic against each other: plateaus of exact ties
+        if abs(score[b] - mine) > 1e-9 * max(abs(mine), 1.0) + 1e-9:
+            problems.append(("score is not the exact score of the returned offset", meta[b], float(score[b]), mine))
+        if st[b] & _native.ALIGN_CAND_OVERFLOW:
+            n_flagged += 1      # a plateau of exact ties wider than the re-score budget: flagged, not checked
+            continue
+        if not (mine >= ws - tol and _score_ok(score[b], ws)):
+            problems.append(("not a maximum", meta[b], mos, int(off[b]), int(wo), mine, ws))
+    assert not problems, problems[:6]
+    # plateaus: constant / period-2 signals against each other, and (unmasked) every all-negative
+    # correlation, whose maximum is the block of structural zeros
+    assert n_flagged <= (12 if mos is not None else 24), n_flagged
