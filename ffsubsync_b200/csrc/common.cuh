@@ -83,6 +83,11 @@ struct b2_ctx {
     uint64_t seq = 0;
     std::vector<float> results;
   } vs;
+  // pageable B2_HOST inputs: two pinned bounce buffers filled by a few host threads (see stage_in)
+  struct Bounce {
+    void* p = nullptr;
+    cudaEvent_t ev = nullptr;
+  } bounce[2];
   cudaStream_t stream2 = nullptr;
   static const int kEvents = 16;
   cudaEvent_t ev_pool[kEvents] = {};
