@@ -78,7 +78,7 @@ def main():
             continue
         os.environ["B2_BIG_WS_MB"] = mb
         out["unmasked_big_ws%s_ms_per_pair" % mb] = timed(lambda: run(None)) / B
-    os.environ.pop("B2_BIG_WS_MB")
+    os.environ.pop("B2_BIG_WS_MB", None)
     print(json.dumps(out))
 
 
