@@ -45,7 +45,7 @@ struct BigJob {          // one (pair, ratio) of the group
   int x_sub, x_ref;      // transform indices inside the group
 };
 
-constexpr int kChunk = 32768;   // offsets per counting CTA
+constexpr int kChunk = 4096;    // offsets per counting CTA
 constexpr int kFineCap = (1 << kMaxQ1) + (1 << (kMaxQ1 - 4)) + (1 << (kMaxQ1 - 8)) + 4;   // skewed size
 constexpr size_t kBigSmemBytes = kSmemBytes + 1024 * 8 + (size_t)kSkew1024 * 8 + (size_t)kFineCap * 8 + 16 * 8 + 64;
 
@@ -330,13 +330,45 @@ __global__ void __launch_bounds__(256) big_select_kernel(const SelJob* __restric
   bool approx_only;
   const float cut = job_cut(job_stat, jb.j, K, winner_only && !job.no_prune, approx_only);
   const float* c = scores + job.score_off;
-  if (tid == 0) scount = 0;
+  // 1. the (at most kCandMax) highest chunks that hold candidates, in descending order, and the total
+  __shared__ int hit_chunk[kCandMax];
+  __shared__ int n_hit, s_total;
+  if (tid == 0) {
+    scount = 0;
+    n_hit = 0;
+    s_total = 0;
+  }
   __syncthreads();
-  int total = 0;
-  for (int ch = n_chunks - 1; ch >= 0; --ch) {
-    const int n_here = chunk_cnt[(size_t)blockIdx.x * n_chunks + ch];
-    total += n_here;
-    if (n_here == 0 || scount >= kCandMax) continue;   // uniform: scount is read after a barrier
+  const int* cnt = chunk_cnt + (size_t)blockIdx.x * n_chunks;
+  for (int top = n_chunks - 1; top >= 0; top -= 256) {
+    const int ch = top - tid;
+    const int here = ch >= 0 ? cnt[ch] : 0;
+    const unsigned ball = __ballot_sync(0xffffffffu, here > 0);
+    int wsum = here;
+    for (int o = 16; o > 0; o >>= 1) wsum += __shfl_xor_sync(0xffffffffu, wsum, o);
+    if ((tid & 31) == 0) {
+      swarp[tid >> 5] = __popc(ball);
+      atomicAdd(&s_total, wsum);
+    }
+    __syncthreads();
+    int before = n_hit;
+    for (int w = 0; w < (tid >> 5); ++w) before += swarp[w];
+    before += __popc(ball & ((1u << (tid & 31)) - 1u));
+    if (here > 0 && before < kCandMax) hit_chunk[before] = ch;
+    __syncthreads();
+    if (tid == 0) {
+      int tot = 0;
+      for (int w = 0; w < 8; ++w) tot += swarp[w];
+      n_hit += tot;
+    }
+    __syncthreads();
+  }
+  const int total = s_total;
+  const int n_walk = min(n_hit, kCandMax);
+  // 2. ordered compaction inside those chunks
+  for (int h = 0; h < n_walk; ++h) {
+    if (scount >= kCandMax) break;   // uniform: scount is read after a barrier
+    const int ch = hit_chunk[h];
     const int lo = max(job.m_lo, ch * kChunk), hi = min(job.m_hi, (ch + 1) * kChunk - 1);
     for (int top = hi; top >= lo; top -= 256) {
       const int m = top - tid;
