@@ -382,14 +382,19 @@ struct BigSource {
 // warps); batches that lie entirely in the zero padding issue no loads.
 constexpr int kLoadBatch = 8;
 CORR_HD float f1_load(float2* buf, const BigSource& src, int q1, int cg, int tid) {
-  const int cl = 14 - q1, c0 = cg << cl, cmask = (1 << cl) - 1;
+  const int cl = 14 - q1;
   const int last = src.len - 1;   // len >= 1 (empty signals never reach the transforms)
+  // sample index of element i of this thread: t(i) = t_base + i * dt (see the note at f1_store)
+  const int t_base = 2 * (((tid >> cl) << 10) + (cg << cl) + (tid & ((1 << cl) - 1)));
+  const int dt = 2 * ((kThreads >> cl) << 10);
+  const int s0 = swz(tid);
   float ss = 0.f;
 #pragma unroll 1
-  for (int e0 = tid; e0 < kM; e0 += kLoadBatch * kThreads) {
-    if (2 * (((e0 >> cl) << 10) + c0 + (e0 & cmask)) >= src.len) {   // n grows with e: the rest is padding
+  for (int i0 = 0; i0 < kM / kThreads; i0 += kLoadBatch) {
+    const int t_first = t_base + i0 * dt;
+    if (t_first >= src.len) {   // t grows with i: the rest of the tile is zero padding
 #pragma unroll
-      for (int i = 0; i < kLoadBatch; ++i) buf[swz(e0 + i * kThreads)] = make_float2(0.f, 0.f);
+      for (int i = 0; i < kLoadBatch; ++i) buf[s0 + (i0 + i) * kThreads] = make_float2(0.f, 0.f);
       continue;
     }
     float2 v[kLoadBatch];
@@ -397,14 +402,12 @@ CORR_HD float f1_load(float2* buf, const BigSource& src, int q1, int cg, int tid
       uint32_t w[kLoadBatch];
 #pragma unroll
       for (int i = 0; i < kLoadBatch; ++i) {
-        const int e = e0 + i * kThreads;
-        const int t0 = 2 * (((e >> cl) << 10) + c0 + (e & cmask));
+        const int t0 = t_first + i * dt;
         w[i] = CORR_LDG(src.bits + ((t0 < last ? t0 : last) >> 5));
       }
 #pragma unroll
       for (int i = 0; i < kLoadBatch; ++i) {
-        const int e = e0 + i * kThreads;
-        const int t0 = 2 * (((e >> cl) << 10) + c0 + (e & cmask));
+        const int t0 = t_first + i * dt;
         const uint32_t m = w[i] >> (t0 & 31);   // t0 even: both bits in one word
         v[i].x = t0 < src.len ? ((m & 1u) ? src.hi : -1.f) : 0.f;
         v[i].y = t0 + 1 < src.len ? ((m & 2u) ? src.hi : -1.f) : 0.f;
@@ -413,15 +416,13 @@ CORR_HD float f1_load(float2* buf, const BigSource& src, int q1, int cg, int tid
       float a[kLoadBatch], b[kLoadBatch];
 #pragma unroll
       for (int i = 0; i < kLoadBatch; ++i) {
-        const int e = e0 + i * kThreads;
-        const int t0 = 2 * (((e >> cl) << 10) + c0 + (e & cmask));
+        const int t0 = t_first + i * dt;
         a[i] = CORR_LDG(src.f + (t0 < last ? t0 : last));
         b[i] = CORR_LDG(src.f + (t0 + 1 < last ? t0 + 1 : last));
       }
 #pragma unroll
       for (int i = 0; i < kLoadBatch; ++i) {
-        const int e = e0 + i * kThreads;
-        const int t0 = 2 * (((e >> cl) << 10) + c0 + (e & cmask));
+        const int t0 = t_first + i * dt;
         v[i].x = t0 < src.len ? 2.f * a[i] - 1.f : 0.f;
         v[i].y = t0 + 1 < src.len ? 2.f * b[i] - 1.f : 0.f;
       }
@@ -429,38 +430,53 @@ CORR_HD float f1_load(float2* buf, const BigSource& src, int q1, int cg, int tid
 #pragma unroll
     for (int i = 0; i < kLoadBatch; ++i) {
       ss += v[i].x * v[i].x + v[i].y * v[i].y;
-      buf[swz(e0 + i * kThreads)] = v[i];
+      buf[s0 + (i0 + i) * kThreads] = v[i];
     }
   }
   return ss;
 }
 // F1 store: four-step twiddle w_M^(n2 k1), rows in natural k1 order.
+// (Element e = tid + 512 i of a thread: swz(e) = swz(tid) + 512 i - the swizzle reads bits 4..7 and
+// writes bits 0..3 only - its column e & (cols - 1) is constant and its row e >> cl advances by
+// 512 >> cl per step: the loops below carry these instead of recomputing them.)
 CORR_HD void f1_store(const float2* buf, const BigTables& bt, int q1, int cg, int tid, float2* g) {
-  const int cl = 14 - q1, c0 = cg << cl, mmask = (1 << (q1 + 10)) - 1;
-  for (int e = tid; e < kM; e += kThreads) {
-    const int p1 = e >> cl, n2 = c0 + (e & ((1 << cl) - 1));
+  const int cl = 14 - q1, mmask = (1 << (q1 + 10)) - 1;
+  const int n2 = (cg << cl) + (tid & ((1 << cl) - 1)), dp = kThreads >> cl;
+  int p1 = tid >> cl, idx = swz(tid);
+#pragma unroll 4
+  for (int i = 0; i < kM / kThreads; ++i, p1 += dp, idx += kThreads) {
     const int k1 = col_freq_of_pos(q1, p1);
-    g[((size_t)k1 << 10) + n2] = cmul(buf[swz(e)], step_twiddle(bt, q1, (int)(((long long)n2 * k1) & mmask)));
+    g[((size_t)k1 << 10) + n2] = cmul(buf[idx], step_twiddle(bt, q1, (n2 * k1) & mmask));
   }
 }
 
 // F2 load / store of the 16 rows of tile g (slot order, see f2_row_of_slot).
 CORR_HD void f2_load(float2* buf, int q1, int g, int tid, const float2* src) {
+  const int s0 = swz(tid);
 #pragma unroll 1
-  for (int e0 = tid; e0 < kM; e0 += kLoadBatch * kThreads) {
+  for (int slot0 = 0; slot0 < 16; slot0 += kLoadBatch / 2) {
     float2 v[kLoadBatch];
 #pragma unroll
-    for (int i = 0; i < kLoadBatch; ++i) {
-      const int e = e0 + i * kThreads;
-      v[i] = CORR_LDG(src + ((size_t)f2_row_of_slot(q1, g, e >> 10) << 10) + (e & 1023));
+    for (int i = 0; i < kLoadBatch / 2; ++i) {
+      const float2* row = src + ((size_t)f2_row_of_slot(q1, g, slot0 + i) << 10);
+      v[2 * i] = CORR_LDG(row + tid);
+      v[2 * i + 1] = CORR_LDG(row + tid + kThreads);
     }
 #pragma unroll
-    for (int i = 0; i < kLoadBatch; ++i) buf[swz(e0 + i * kThreads)] = v[i];
+    for (int i = 0; i < kLoadBatch / 2; ++i) {
+      buf[s0 + (slot0 + i) * 1024] = v[2 * i];
+      buf[s0 + (slot0 + i) * 1024 + kThreads] = v[2 * i + 1];
+    }
   }
 }
 CORR_HD void f2_store(const float2* buf, int q1, int g, int tid, float2* dst) {
-  for (int e = tid; e < kM; e += kThreads)
-    dst[((size_t)f2_row_of_slot(q1, g, e >> 10) << 10) + (e & 1023)] = buf[swz(e)];
+  const int s0 = swz(tid);
+#pragma unroll 4
+  for (int slot = 0; slot < 16; ++slot) {
+    float2* row = dst + ((size_t)f2_row_of_slot(q1, g, slot) << 10);
+    row[tid] = buf[s0 + slot * 1024];
+    row[tid + kThreads] = buf[s0 + slot * 1024 + kThreads];
+  }
 }
 // row_tw[slot] = exp(-i pi k1 / M): threads 0..15
 CORR_HD void f2_row_twiddles(float2* row_tw, int q1, int g, int tid) {
@@ -533,44 +549,51 @@ CORR_HD void f2_product_inplace(float2* buf, const BigTables& bt, int q1, int g,
 // F2 (subtitles) store after the inverse row transform: conjugate four-step twiddle.
 CORR_HD void f2_store_twiddled(const float2* buf, const BigTables& bt, int q1, int g, int tid, float2* dst) {
   const int mmask = (1 << (q1 + 10)) - 1;
-  for (int e = tid; e < kM; e += kThreads) {
-    const int k1 = f2_row_of_slot(q1, g, e >> 10), n2 = e & 1023;
-    dst[((size_t)k1 << 10) + n2] =
-        cmul(buf[swz(e)], cconj(step_twiddle(bt, q1, (int)(((long long)n2 * k1) & mmask))));
+  const int s0 = swz(tid);
+#pragma unroll 2
+  for (int slot = 0; slot < 16; ++slot) {
+    const int k1 = f2_row_of_slot(q1, g, slot);
+    float2* row = dst + ((size_t)k1 << 10);
+    const int x0 = (tid * k1) & mmask, x1 = (x0 + kThreads * k1) & mmask;   // n2 = tid, tid + 512
+    row[tid] = cmul(buf[s0 + slot * 1024], cconj(step_twiddle(bt, q1, x0)));
+    row[tid + kThreads] = cmul(buf[s0 + slot * 1024 + kThreads], cconj(step_twiddle(bt, q1, x1)));
   }
 }
 
 // F3 load: columns of the k1-major array into row positions (digit-reversed for the inverse passes).
 CORR_HD void f3_load(float2* buf, int q1, int cg, int tid, const float2* g) {
-  const int cl = 14 - q1, c0 = cg << cl;
+  const int cl = 14 - q1, dp = kThreads >> cl;
+  const float2* col = g + (cg << cl) + (tid & ((1 << cl) - 1));
+  const int s0 = swz(tid), p0 = tid >> cl;
 #pragma unroll 1
-  for (int e0 = tid; e0 < kM; e0 += kLoadBatch * kThreads) {
+  for (int i0 = 0; i0 < kM / kThreads; i0 += kLoadBatch) {
     float2 v[kLoadBatch];
 #pragma unroll
-    for (int i = 0; i < kLoadBatch; ++i) {
-      const int e = e0 + i * kThreads;
-      v[i] = CORR_LDG(g + ((size_t)col_freq_of_pos(q1, e >> cl) << 10) + c0 + (e & ((1 << cl) - 1)));
-    }
+    for (int i = 0; i < kLoadBatch; ++i)
+      v[i] = CORR_LDG(col + ((size_t)col_freq_of_pos(q1, p0 + (i0 + i) * dp) << 10));
 #pragma unroll
-    for (int i = 0; i < kLoadBatch; ++i) buf[swz(e0 + i * kThreads)] = v[i];
+    for (int i = 0; i < kLoadBatch; ++i) buf[s0 + (i0 + i) * kThreads] = v[i];
   }
 }
 // F3 store: c[2n], c[2n+1] = re, im of z[n]; score index m = (lag + S) mod N (offset o = m - S).
 // mx: maximum over the surviving window [m_lo, m_hi]; cn: sum of squares of everything written.
 CORR_HD void f3_store(const float2* buf, int q1, int cg, int tid, float* scores, int S, int m_lo, int m_hi,
                       float& mx, float& cn) {
-  const int cl = 14 - q1, c0 = cg << cl;
+  const int cl = 14 - q1;
   const int nmask = (2 << (q1 + 10)) - 1;
   const float sc = out_scale(q1);
-  for (int e = tid; e < kM; e += kThreads) {
-    const int n = ((e >> cl) << 10) + c0 + (e & ((1 << cl) - 1));
-    const float2 z = buf[swz(e)];
+  const int n0 = ((tid >> cl) << 10) + (cg << cl) + (tid & ((1 << cl) - 1));
+  const int dm = 2 * ((kThreads >> cl) << 10);   // score-index step between consecutive elements of a thread
+  int m = (2 * n0 + S) & nmask, idx = swz(tid);
+#pragma unroll 4
+  for (int i = 0; i < kM / kThreads; ++i, m = (m + dm) & nmask, idx += kThreads) {
+    const float2 z = buf[idx];
     const float v0 = z.x * sc, v1 = z.y * sc;
-    const int m0 = (2 * n + S) & nmask, m1 = (2 * n + 1 + S) & nmask;
-    scores[m0] = v0;
+    const int m1 = (m + 1) & nmask;
+    scores[m] = v0;
     scores[m1] = v1;
     cn += v0 * v0 + v1 * v1;
-    if (m0 >= m_lo && m0 <= m_hi) mx = fmaxf(mx, v0);
+    if (m >= m_lo && m <= m_hi) mx = fmaxf(mx, v0);
     if (m1 >= m_lo && m1 <= m_hi) mx = fmaxf(mx, v1);
   }
 }
