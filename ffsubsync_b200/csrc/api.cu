@@ -281,9 +281,19 @@ static void parallel_memcpy(void* dst, const void* src, size_t bytes) {
   const size_t per = ((bytes / kCopyThreads) + 4095) & ~(size_t)4095;
   std::thread th[kCopyThreads];
   int n = 0;
-  for (size_t off = per; off < bytes && n < kCopyThreads - 1; off += per, ++n)
-    th[n] = std::thread([=] { memcpy((char*)dst + off, (const char*)src + off, std::min(per, bytes - off)); });
-  memcpy(dst, src, std::min(per, bytes));
+  size_t mine_end = std::min(per, bytes);   // this thread copies [0, mine_end) and whatever could not be handed out
+  for (size_t off = per; off < bytes && n < kCopyThreads - 1; off += per) {
+    const size_t len = (n == kCopyThreads - 2) ? bytes - off : std::min(per, bytes - off);
+    try {
+      th[n] = std::thread([=] { memcpy((char*)dst + off, (const char*)src + off, len); });
+      ++n;
+    } catch (...) {   // no thread to be had (resource limits): nothing may escape through the C ABI
+      memcpy((char*)dst + off, (const char*)src + off, bytes - off);
+      break;
+    }
+    if (off + len >= bytes) break;
+  }
+  memcpy(dst, src, mine_end);
   for (int i = 0; i < n; ++i) th[i].join();
 }
 
