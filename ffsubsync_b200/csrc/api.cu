@@ -5,6 +5,7 @@
 #include <math.h>
 
 #include <algorithm>
+#include <atomic>
 #include <thread>
 
 #include "common.cuh"
@@ -266,7 +267,7 @@ static cudaEvent_t next_event(b2_ctx* h) {
 // 4.2 ms from pinned memory, profiles/r2e_latency_single_pair.json).  Here the copy goes through two
 // pinned 32 MB buffers filled by kCopyThreads host threads while the previous buffer is on the bus.
 static const size_t kBounceBytes = (size_t)32 << 20;
-static const int kCopyThreads = 4;
+static const int kCopyThreads = 6;
 
 static bool is_pageable(const void* p) {
   cudaPointerAttributes at;
@@ -277,24 +278,20 @@ static bool is_pageable(const void* p) {
   return at.type == cudaMemoryTypeUnregistered;
 }
 
-static void parallel_memcpy(void* dst, const void* src, size_t bytes) {
-  const size_t per = ((bytes / kCopyThreads) + 4095) & ~(size_t)4095;
-  std::thread th[kCopyThreads];
-  int n = 0;
-  size_t mine_end = std::min(per, bytes);   // this thread copies [0, mine_end) and whatever could not be handed out
-  for (size_t off = per; off < bytes && n < kCopyThreads - 1; off += per) {
-    const size_t len = (n == kCopyThreads - 2) ? bytes - off : std::min(per, bytes - off);
-    try {
-      th[n] = std::thread([=] { memcpy((char*)dst + off, (const char*)src + off, len); });
-      ++n;
-    } catch (...) {   // no thread to be had (resource limits): nothing may escape through the C ABI
-      memcpy((char*)dst + off, (const char*)src + off, bytes - off);
-      break;
-    }
-    if (off + len >= bytes) break;
-  }
-  memcpy(dst, src, mine_end);
-  for (int i = 0; i < n; ++i) th[i].join();
+// Copy workers live for one staged transfer: worker t copies slice t of every chunk into the bounce
+// buffer the main thread announces (`ready`), and reports through `done`; the main thread turns each
+// filled buffer into an async H2D copy.  No thread is created per chunk; the only blocking wait is
+// on the event of the H2D copy that last read the buffer.
+struct CopyCrew {
+  std::atomic<int> ready{-1};           // index of the chunk whose bounce buffer may be filled
+  std::atomic<int> done{0};             // slices finished, over all chunks
+  std::atomic<bool> abort{false};
+};
+
+static void copy_slice(char* dst, const char* src, size_t n, int t, int nthreads) {
+  const size_t per = ((n / nthreads) + 4095) & ~(size_t)4095;
+  const size_t lo = std::min(n, per * (size_t)t), hi = t == nthreads - 1 ? n : std::min(n, per * (size_t)(t + 1));
+  if (hi > lo) memcpy(dst + lo, src + lo, hi - lo);
 }
 
 static int staged_h2d(b2_ctx* h, void* dev, const void* host, size_t bytes) {
@@ -303,15 +300,49 @@ static int staged_h2d(b2_ctx* h, void* dev, const void* host, size_t bytes) {
       B2_CUDA(h, cudaMallocHost(&b.p, kBounceBytes));
       B2_CUDA(h, cudaEventCreateWithFlags(&b.ev, cudaEventDisableTiming));
     }
-  int i = 0;
-  for (size_t off = 0; off < bytes; off += kBounceBytes, ++i) {
-    b2_ctx::Bounce& b = h->bounce[i & 1];
-    const size_t n = std::min(kBounceBytes, bytes - off);
-    B2_CUDA(h, cudaEventSynchronize(b.ev));   // the copy that last read this buffer (no-op the first time)
-    parallel_memcpy(b.p, (const char*)host + off, n);
-    B2_CUDA(h, cudaMemcpyAsync((char*)dev + off, b.p, n, cudaMemcpyHostToDevice, h->stream));
-    B2_CUDA(h, cudaEventRecord(b.ev, h->stream));
+  const int n_chunks = (int)((bytes + kBounceBytes - 1) / kBounceBytes);
+  CopyCrew crew;
+  std::thread workers[kCopyThreads];
+  int n_workers = 0;   // helpers besides this thread (slice 0 is copied here)
+  auto work = [&](int t, int nthreads) {
+    for (int c = 0; c < n_chunks; ++c) {
+      while (crew.ready.load(std::memory_order_acquire) < c) {
+        if (crew.abort.load(std::memory_order_relaxed)) return;
+        std::this_thread::yield();
+      }
+      const size_t off = (size_t)c * kBounceBytes, n = std::min(kBounceBytes, bytes - off);
+      copy_slice((char*)h->bounce[c & 1].p, (const char*)host + off, n, t, nthreads);
+      crew.done.fetch_add(1, std::memory_order_release);
+    }
+  };
+  try {
+    for (; n_workers < kCopyThreads - 1; ++n_workers) workers[n_workers] = std::thread(work, n_workers + 1, kCopyThreads);
+  } catch (...) {   // no more threads to be had: nothing may escape through the C ABI
+    crew.abort.store(true);
+    for (int i = 0; i < n_workers; ++i) workers[i].join();
+    n_workers = 0;
+    crew.abort.store(false);
   }
+  const int nthreads = n_workers == kCopyThreads - 1 ? kCopyThreads : 1;   // all helpers or none
+  int status = B2_OK;
+  for (int c = 0; c < n_chunks && status == B2_OK; ++c) {
+    b2_ctx::Bounce& b = h->bounce[c & 1];
+    const size_t off = (size_t)c * kBounceBytes, n = std::min(kBounceBytes, bytes - off);
+    if (cudaEventSynchronize(b.ev) != cudaSuccess) {   // the copy that last read this buffer
+      status = B2_ERR_CUDA;
+      break;
+    }
+    crew.ready.store(c, std::memory_order_release);
+    copy_slice((char*)b.p, (const char*)host + off, n, 0, nthreads);
+    while (crew.done.load(std::memory_order_acquire) < (c + 1) * (nthreads - 1)) std::this_thread::yield();
+    if (cudaMemcpyAsync((char*)dev + off, b.p, n, cudaMemcpyHostToDevice, h->stream) != cudaSuccess ||
+        cudaEventRecord(b.ev, h->stream) != cudaSuccess)
+      status = B2_ERR_CUDA;
+  }
+  if (status != B2_OK) crew.abort.store(true);
+  crew.ready.store(n_chunks, std::memory_order_release);
+  for (int i = 0; i < n_workers; ++i) workers[i].join();
+  if (status != B2_OK) B2_FAIL(h, status, "staged host-to-device copy failed: %s", cudaGetErrorString(cudaGetLastError()));
   return B2_OK;
 }
 
