@@ -380,7 +380,7 @@ struct BigSource {
 // thread with clamped (always valid) addresses and masked afterwards, so that the loads of a batch are
 // in flight together (one 512-thread CTA per SM covers the latency with loads in flight, not with
 // warps); batches that lie entirely in the zero padding issue no loads.
-constexpr int kLoadBatch = 8;
+constexpr int kLoadBatch = 16;
 CORR_HD float f1_load(float2* buf, const BigSource& src, int q1, int cg, int tid) {
   const int cl = 14 - q1;
   const int last = src.len - 1;   // len >= 1 (empty signals never reach the transforms)
@@ -524,26 +524,70 @@ CORR_HD void product_visit(float2* buf, const PairGeo& pg, float2 bp, float2 bq)
   buf[ia] = np;
   if (pg.kind == 0) buf[ib] = nq;
 }
+// Regular slot pair (s, 8 + s) of a thread: its two pairs are (s, p) <-> (8 + s, 1023 - p) for p = tid and
+// p = tid + 512.  Everything that depends on the thread only (swizzled offsets inside a row, the k2
+// part of the twiddle) is computed once per call, everything that depends on the slot (row base
+// pointers, the k1 part of the twiddle) once per slot.
+struct PairLanes {
+  int ia0, ib0, ia1, ib1;   // swizzled in-row indices of the two pairs (add slot * 1024 / (8 + slot) * 1024)
+  float2 h0, h1;            // half_pos[tid], half_pos[tid + 512]
+};
+CORR_HD PairLanes pair_lanes(const BigTables& bt, int tid) {
+  PairLanes l;
+  l.ia0 = swz(tid);
+  l.ib0 = swz(1023 - tid);
+  l.ia1 = swz(tid + kThreads);
+  l.ib1 = swz(1023 - tid - kThreads);
+  l.h0 = bt.half_pos[tid];
+  l.h1 = bt.half_pos[tid + kThreads];
+  return l;
+}
+CORR_HD void product_regular(float2* buf, int ia, int ib, float2 w, float2 bp, float2 bq) {
+  const float2 zp = buf[ia], zq = buf[ib];
+  float2 hp, hq;
+  untangle_bins(zp, zq, w, hp, hq);
+  float2 np, nq;
+  retangle_bins(cmul_conj_a(hp, bp), cmul_conj_a(hq, bq), w, np, nq);
+  buf[ia] = np;
+  buf[ib] = nq;
+}
 CORR_HD void f2_product_inplace(float2* buf, const BigTables& bt, int q1, int g, const float2* row_tw, int tid,
                                 const float2* spec) {
-  constexpr int kB = 4;   // pairs per batch: 8 spectrum loads in flight per thread
+  const PairLanes l = pair_lanes(bt, tid);
+  constexpr int kS = 4;   // slot pairs per batch: 16 spectrum loads in flight per thread
 #pragma unroll 1
-  for (int it0 = 0; it0 < kPairSlotsPerThread; it0 += kB) {
-    PairGeo pg[kB];
-    float2 bp[kB], bq[kB];
+  for (int s0 = 0; s0 < 8; s0 += kS) {
+    float2 bp0[kS], bq0[kS], bp1[kS], bq1[kS];
 #pragma unroll
-    for (int i = 0; i < kB; ++i) {
-      pg[i] = f2_pair(bt, g, row_tw, tid + (it0 + i) * kThreads);
-      bp[i] = CORR_LDG(spec + spec_index(q1, g, pg[i].ea));
-      bq[i] = CORR_LDG(spec + spec_index(q1, g, pg[i].eb));
+    for (int i = 0; i < kS; ++i) {
+      const int s = s0 + i;
+      if (g == 0 && s == 0) continue;   // the two self-paired rows: general path below
+      const float2* ra = spec + ((size_t)f2_row_of_slot(q1, g, s) << 10);
+      const float2* rb = spec + ((size_t)f2_row_of_slot(q1, g, 8 + s) << 10);
+      bp0[i] = CORR_LDG(ra + tid);
+      bq0[i] = CORR_LDG(rb + 1023 - tid);
+      bp1[i] = CORR_LDG(ra + tid + kThreads);
+      bq1[i] = CORR_LDG(rb + 1023 - tid - kThreads);
     }
 #pragma unroll
-    for (int i = 0; i < kB; ++i) product_visit(buf, pg[i], bp[i], bq[i]);
+    for (int i = 0; i < kS; ++i) {
+      const int s = s0 + i;
+      if (g == 0 && s == 0) continue;
+      const float2 rt = row_tw[s];
+      product_regular(buf, s * 1024 + l.ia0, (8 + s) * 1024 + l.ib0, cmul(rt, l.h0), bp0[i], bq0[i]);
+      product_regular(buf, s * 1024 + l.ia1, (8 + s) * 1024 + l.ib1, cmul(rt, l.h1), bp1[i], bq1[i]);
+    }
   }
-  if (g == 0 && tid == 0) {
-    const PairGeo pg = f2_extra_pair(bt, row_tw);
-    const float2 b = CORR_LDG(spec + spec_index(q1, g, pg.ea));
-    product_visit(buf, pg, b, b);
+  if (g == 0) {   // tile 0: rows 0 and M1/2 pair with themselves (slots 0 and 8), plus the bin k = M/2
+    for (int h = 0; h < 2; ++h) {
+      const PairGeo pg = f2_pair(bt, g, row_tw, tid + h * kThreads);
+      product_visit(buf, pg, CORR_LDG(spec + spec_index(q1, g, pg.ea)), CORR_LDG(spec + spec_index(q1, g, pg.eb)));
+    }
+    if (tid == 0) {
+      const PairGeo pg = f2_extra_pair(bt, row_tw);
+      const float2 b = CORR_LDG(spec + spec_index(q1, g, pg.ea));
+      product_visit(buf, pg, b, b);
+    }
   }
 }
 // F2 (subtitles) store after the inverse row transform: conjugate four-step twiddle.
