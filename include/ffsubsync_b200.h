@@ -9,8 +9,10 @@
  *
  * Conventions
  *   - every function returns B2_OK (0) or a negative b2_status; b2_last_error(h) gives text.
- *   - "memspace" says where the BULK arrays of that call live: B2_HOST (the library stages
- *     them through pinned memory, copies results back and synchronises before returning) or
+ *   - "memspace" says where the BULK arrays of that call live: B2_HOST (the library copies them
+ *     to the device - directly from pinned memory; large pageable buffers through its own pinned
+ *     double buffer filled by a few host threads - copies results back and synchronises before
+ *     returning) or
  *     B2_DEVICE (pointers are device pointers on the handle's device - a pointer that belongs to
  *     another device is rejected with B2_ERR_BAD_ARG; the call only enqueues work on the handle's
  *     stream and does not synchronise).  Calls leave the caller thread's current CUDA device as
