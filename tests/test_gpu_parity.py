@@ -493,6 +493,9 @@ def test_sync_batch_unmasked_vs_oracle(handle):
             sub = ro.rasterize(pairs.cue_start[c0:c1], pairs.cue_end[c0:c1], None, 100, 0, r)[0]
             ws, wo = ao.fft_align(ref, sub, None)
             assert res[4][b * 5 + k] == wo and _score_ok(res[3][b * 5 + k], ws), (b, k)
+    # winner-only run (ratios that provably cannot win keep their fp32 result): same best triples
+    win = bs.sync_host(pcm, pairs.win_off * 160, pairs.cue_start, pairs.cue_end, pairs.cue_off)
+    assert all(np.array_equal(a, b) for a, b in zip(win[:3], res[:3]))
 
 
 def test_align_multi_segment_grid(handle, golden, golden_arrays, gf):
@@ -856,6 +859,21 @@ def test_auditok_detector_matches_oracle(handle, frame_rate, label):
     # the literal (per-block numpy validator) restatement on a shorter input
     pcm = _auditok_pcm(rng, frame_rate, 1200, 5)
     assert np.array_equal(det(pcm.tobytes()), au.auditok_detect(pcm.tobytes(), 100, frame_rate, label))
+
+
+def test_auditok_one_long_call(handle):
+    """A whole 30-minute signal in ONE detector call (180 000 blocks through one warp's scan), and the
+    same signal through the batch ABI in 100 s calls."""
+    from ffsubsync_b200.speech_transformers import _make_auditok_detector
+    from oracle import auditok_oracle as au
+    rng = np.random.RandomState(180)
+    pcm = _auditok_pcm(rng, 16000, 180000, cut=3)
+    got = _make_auditok_detector(100, 16000, 0.0)(pcm.tobytes())
+    assert np.array_equal(got, au.auditok_detect_fast(pcm.tobytes(), 100, 16000, 0.0))
+    out, _ = handle.vad_auditok(pcm, [0, len(pcm)], 16000, 100, 0.0, chunk_samples=160 * 10000)
+    want = np.concatenate([au.auditok_detect_fast(pcm[i:i + 1600000].tobytes(), 100, 16000, 0.0)
+                           for i in range(0, len(pcm), 1600000)])
+    assert np.array_equal(out, want)
 
 
 def test_energy_rule_equals_the_auditok_validator(handle):
