@@ -926,7 +926,7 @@ extern "C" int b2_sync_batch(b2_handle h, const int16_t* pcm, const int64_t* pcm
   int32_t* o_bo = memspace == B2_DEVICE ? best_offset : d_bo;
   int32_t* o_bk = memspace == B2_DEVICE ? best_k : d_bk;
   // only the best ratio of each pair is reported unless the per-ratio arrays are requested:
-  // ratios that provably cannot win are then not re-scored exactly (B2_ALIGN_APPROX)
+  // ratios that cannot win even after the round-off bound tau are then not re-scored exactly (B2_ALIGN_APPROX)
   const int winner_only = (!all_score && !all_offset) ? 1 : 0;
 
   // Software pipeline over sub-batches of pairs: the VAD of sub-batch i+1 (HBM-bound, caller's

@@ -258,7 +258,7 @@ __global__ void big_init_stat_kernel(float2* __restrict__ job_stat, int n) {
   if (j < n) job_stat[j] = make_float2(-INFINITY, 0.f);
 }
 
-// The cut of a job: fp32 maximum minus tau; with winner_only a ratio that provably cannot be the
+// The cut of a job: fp32 maximum minus tau; with winner_only a ratio that by the bound tau cannot be the
 // pair's best keeps only its fp32 argmax (same rule as select_candidates_kernel in corr.cu).
 __device__ __forceinline__ float job_cut(const float2* __restrict__ job_stat, int j, int K, int winner_only,
                                          bool& approx_only) {
