@@ -52,8 +52,9 @@ enum {
   B2_ALIGN_EMPTY = 1,        /* reference or subtitle signal has length 0 */
   B2_ALIGN_ALL_MASKED = 2,   /* max_offset mask left nothing: score = -inf, offset = N-1-S */
   B2_ALIGN_CAND_OVERFLOW = 4, /* more near-maximal candidates than the re-score budget (flag) */
-  B2_ALIGN_APPROX = 8 /* b2_sync_batch without per-ratio outputs: this ratio cannot be (its fp32 maximum plus the round-off bound tau lies below another ratio's maximum minus tau)
-                         the pair's best, so it was not re-scored; fp32 score / its argmax kept */
+  B2_ALIGN_APPROX = 8 /* b2_sync_batch without per-ratio outputs: this ratio cannot be the pair's best
+                         (its fp32 maximum plus the round-off bound tau lies below another ratio's
+                         maximum minus tau), so it was not re-scored; fp32 score / its argmax kept */
 };
 
 /* FFTAligner(max_offset_samples=None).  Every other int64 value is a mask width and goes through the
