@@ -1135,3 +1135,14 @@ def test_adversarial_families_offsets_are_exact_maxima(handle, mos):
     # each other and, unmasked, every all-negative correlation, whose maximum is the block of structural
     # zeros.  Measured: 16 of 36 (masked), <= 24 (unmasked).
     assert n_flagged <= 24, n_flagged
+
+
+def test_unmasked_largest_transform_size(handle):
+    """N = 2^23 (M1 = 4096, the largest four-step factorisation): R + S = 5.5 M frames (15 h of signal)."""
+    from ffsubsync_b200.aligners import FFTAligner
+    rng = np.random.RandomState(23)
+    ref = (rng.rand(3000000) > 0.5).astype(np.float32)
+    sub = np.concatenate([np.zeros(4321, np.float32), ref])[:2500001]
+    score, off = FFTAligner().fit_transform(ref, sub, get_score=True)
+    ws, wo = ao.fft_align(ref, sub, None)
+    assert off == wo == -4321 and _score_ok(score, ws)
