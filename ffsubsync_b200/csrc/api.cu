@@ -83,6 +83,8 @@ extern "C" int b2_destroy(b2_handle h) {
     if (w.p) cudaFree(w.p);
   for (auto& p : h->pinned)
     if (p.p) cudaFreeHost(p.p);
+  for (auto& e : h->pinned_ev)
+    if (e) cudaEventDestroy(e);
   for (auto& b : h->bounce) {
     if (b.p) cudaFreeHost(b.p);
     if (b.ev) cudaEventDestroy(b.ev);

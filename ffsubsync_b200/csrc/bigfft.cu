@@ -496,11 +496,17 @@ int b2i_align_big(b2_ctx* h, const float* d_ref, const float* d_sub, const uint3
   }
   // The job table is read by kernels of EVERY group and by the common tail, i.e. long after later
   // metadata arenas have been committed - outside the reuse contract of the arena ring (a slot may be
-  // recycled 8 arenas later).  It lives in its own workspace; the copy from pageable memory is staged
-  // by the runtime before the call returns.
-  void* d_selv;
+  // recycled 8 arenas later).  It lives in its own workspace.
+  void *d_selv, *h_selv;
   B2_TRY(b2i_ws(h, b2_ctx::WS_META, J * sizeof(SelJob) + 256, &d_selv));
-  B2_CUDA(h, cudaMemcpyAsync(d_selv, sel.data(), J * sizeof(SelJob), cudaMemcpyHostToDevice, h->stream));
+  // staged through a pinned buffer of the handle (a copy from pageable memory would first wait for
+  // the stream to drain); the event guards the buffer against the next call
+  if (!h->pinned_ev[0]) B2_CUDA(h, cudaEventCreateWithFlags(&h->pinned_ev[0], cudaEventDisableTiming));
+  B2_CUDA(h, cudaEventSynchronize(h->pinned_ev[0]));
+  B2_TRY(b2i_pinned(h, 0, J * sizeof(SelJob) + 256, &h_selv));
+  memcpy(h_selv, sel.data(), J * sizeof(SelJob));
+  B2_CUDA(h, cudaMemcpyAsync(d_selv, h_selv, J * sizeof(SelJob), cudaMemcpyHostToDevice, h->stream));
+  B2_CUDA(h, cudaEventRecord(h->pinned_ev[0], h->stream));
   const SelJob* d_sel = (const SelJob*)d_selv;
   *d_sel_out = d_sel;
   B2_CUDA(h, cudaMemsetAsync(cb.work_count, 0, sizeof(int), h->stream));

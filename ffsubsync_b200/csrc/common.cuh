@@ -48,6 +48,7 @@ struct b2_ctx {
          WS_SIG_REF, WS_SIG_SUB, WS_MISC, WS_COUNTERS, WS_COUNT };
   DeviceBuf ws[WS_COUNT];
   HostBuf pinned[4];
+  cudaEvent_t pinned_ev[4] = {};   // recorded after the last async copy out of pinned[i]
   // ring of metadata upload buffers (see b2i_meta_begin)
   static const int kMetaSlots = 8;
   struct MetaSlot {
