@@ -416,7 +416,7 @@ def run_gpu(args):
             traffic_src = ("ncu --set full dram__bytes_read.sum + dram__bytes_write.sum of a %d-pair launch "
                            "(%s), x%.4f of its algorithmic bytes, scaled to this launch's pairs"
                            % (tr["pairs"], tr["source"], ratio))
-        roofline = {"kernel": "vad_energy_zcr_kernel", "bound": "hbm", "achieved": achieved, "peak": peak,
+        roofline = {"kernel": "vad_lane_kernel<20, 1> (b2_vad_energy_zcr over the whole batch, all SMs)", "bound": "hbm", "achieved": achieved, "peak": peak,
                     "unit": "GB/s", "frac": achieved / peak, "traffic": traffic, "traffic_source": traffic_src,
                     "peak_source": peak_src,
                     "frac_note": "the peak is a COPY bandwidth (read+write mix); this kernel is 98.8 %% reads, "
@@ -425,7 +425,9 @@ def run_gpu(args):
                     "algorithmic_bytes_per_launch": BYTES_VAD * B,
                     "stages_note": "stages_ms time b2_vad_energy_zcr / b2_rasterize / b2_align_batch called "
                                    "one by one; the timed step calls b2_sync_batch, which replaces the float "
-                                   "rasteriser by bit masks (no rasterize_ms on that path)",
+                                   "rasteriser by bit masks (no rasterize_ms on that path) and, from 96 pairs on, "
+                                   "runs the VAD of sub-batches 2 and 3 on 80 SMs beside the alignment of the "
+                                   "previous sub-batch (the step is shorter than vad_ms + align_ms)",
                     "whole_path": {"achieved": (BYTES_VAD + bytes_align(K)) * B * steps
                                    / (elapsed_ms * 1e-3) / 1e9 if world == 1 else None,
                                    "unit": "GB/s (algorithmic bytes of VAD + align over the step time)"}}

@@ -58,7 +58,11 @@ extern "C" int b2_create(int device, b2_handle* out) {
     return B2_ERR_CUDA;
   }
   h->own_stream = true;
-  if (cudaStreamCreateWithFlags(&h->stream2, cudaStreamNonBlocking) != cudaSuccess) {
+  // internal second stream at the highest priority: when b2_sync_batch pipelines sub-batches, the VAD CTAs
+  // queued on it take the SMs that the (lower-priority) correlation CTAs of the caller's stream give up
+  int prio_lo = 0, prio_hi = 0;
+  cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi);
+  if (cudaStreamCreateWithPriority(&h->stream2, cudaStreamNonBlocking, prio_hi) != cudaSuccess) {
     cudaStreamDestroy(h->stream);
     delete h;
     return B2_ERR_CUDA;
@@ -931,68 +935,73 @@ extern "C" int b2_sync_batch(b2_handle h, const int16_t* pcm, const int64_t* pcm
   // ratios that cannot win even after the round-off bound tau are then not re-scored exactly (B2_ALIGN_APPROX)
   const int winner_only = (!all_score && !all_offset) ? 1 : 0;
 
-  // Software pipeline over sub-batches of pairs: the VAD of sub-batch i+1 (HBM-bound, caller's
-  // stream) runs while sub-batch i is rasterised / correlated / reduced (FP32- and shared-memory
-  // bound, internal stream2).  The two kernels are sized to co-reside on an SM (VAD: 82 KB smem,
-  // 9 K registers; correlation: 139 KB, 48 K registers, accumulators in tensor memory).
-  // Measured on B200 (tools/overlap_probe.py, profiles/README.md): the VAD needs both of its CTAs
-  // per SM (16 consumer warps) to reach 5.9 TB/s - with one CTA it runs at 58 % - so sharing the
-  // SM costs more than the overlap returns (148 pairs: 9.55 ms unpipelined, 11.6 ms with 3
-  // sub-batches).  The pipeline therefore stays OFF by default (n_sub = 1); B2_SUBBATCHES=n enables
-  // it for experiments and tests/test_gpu_parity.py keeps it bit-identical.
-  int n_sub = 1;
-  const char* ns_env = getenv("B2_SUBBATCHES");
-  if (ns_env) n_sub = std::max(1, std::min(B, atoi(ns_env)));
-  // make sure the workspaces that stream2 grows are not reallocated under the other stream
-  cudaEvent_t done2 = nullptr;
-  for (int i = 0; i < n_sub; ++i) {
-    const int b0 = (int)((int64_t)B * i / n_sub), b1 = (int)((int64_t)B * (i + 1) / n_sub);
-    if (b1 == b0) continue;
-    const int nb = b1 - b0;
-    {
-      // the first sub-batch has nothing to overlap with: full VAD occupancy; later ones leave
-      // room for the correlation CTAs of the previous sub-batch
-      const char* vc = getenv("B2_VAD_CTAS");
-      h->vad_ctas_per_sm = (n_sub > 1 && i > 0) ? (vc ? atoi(vc) : 1) : 0;
-      const int st = b2i_vad_launch(h, d_pcm, pcm_off + b0, nb, fpw, non_speech_label,
-                                    (int64_t)fpw * energy_threshold, z_lo, z_hi, (float*)d_refsig,
-                                    ref_off.data() + b0);
-      h->vad_ctas_per_sm = 0;
-      if (st != B2_OK) return st;
-    }
-    if (n_sub == 1) {
-      if (!fused)
-        B2_TRY(b2i_raster_launch(h, cue_start_s, cue_end_s, cue_keep, cue_off, B, ratios, K, 0, nullptr,
-                                 sample_rate, start_seconds, (float*)d_subsig, sub_off.data()));
-      B2_TRY(b2i_align_launch(h, (const float*)d_refsig, ref_off.data(), (const float*)d_subsig,
-                              sub_off.data(), B, K, max_offset_samples, o_score, o_offset, d_status,
-                              winner_only, fused ? &cue_src : nullptr));
-      B2_TRY(b2i_reduce_launch(h, o_score, o_offset, d_status, B, K, max_offset_samples, o_bs, o_bo,
-                               o_bk));
-      break;
-    }
-    cudaEvent_t vad_done = next_event(h);
-    B2_CUDA(h, cudaEventRecord(vad_done, h->stream));
+  // Software pipeline over sub-batches of pairs.  The VAD (HBM-bound) of every sub-batch is queued on the
+  // internal high-priority stream: sub-batch 0 on the whole GPU, the later ones on `vad_sms` SMs only (one
+  // lane-per-window CTA per SM, csrc/vad.cu); the rasterisation / correlation / reduction of sub-batch i
+  // (FP32- and shared-memory bound) follows on the caller's stream as soon as its VAD is done and runs on
+  // the SMs the VAD leaves free - a VAD CTA owns its SM's shared memory, so the block scheduler keeps the
+  // two apart.  Needs the lane-per-window kernel (1.3 instructions per byte: ~80 GB/s per SM); with the
+  // lane-group kernel (every SM's issue slots to reach the HBM roofline) partitioning never paid
+  // (profiles/r2a_partition_probe.txt).  B2_SUBBATCHES / B2_VAD_SMS override the defaults; 1 / 0 = off.
+  // Defaults (measured on 256 two-hour pairs, tools/pipeline_probe.py: 3 sub-batches x 80 of 148 SMs =
+  // 11.16 ms per step against 12.49 unpipelined; 2-6 sub-batches and 74-86 SMs are within 4 %); small
+  // batches stay unpipelined (the alignment of a third of a small batch is launch- and tail-bound).
+  int n_sub = 1, vad_sms = 0;
+  if (B >= 96 && b2i_vad_lane_eligible(pcm_off, B, fpw)) {
+    n_sub = 3;
+    vad_sms = (h->sm_count * 80 + 74) / 148;
+  }
+  if (const char* e = getenv("B2_SUBBATCHES")) n_sub = std::max(1, std::min(B, atoi(e)));
+  if (const char* e = getenv("B2_VAD_SMS")) vad_sms = std::max(0, std::min(h->sm_count, atoi(e)));
+  if (n_sub == 1) {
+    B2_TRY(b2i_vad_launch(h, d_pcm, pcm_off, B, fpw, non_speech_label, (int64_t)fpw * energy_threshold, z_lo,
+                          z_hi, (float*)d_refsig, ref_off.data()));
+    if (!fused)
+      B2_TRY(b2i_raster_launch(h, cue_start_s, cue_end_s, cue_keep, cue_off, B, ratios, K, 0, nullptr,
+                               sample_rate, start_seconds, (float*)d_subsig, sub_off.data()));
+    B2_TRY(b2i_align_launch(h, (const float*)d_refsig, ref_off.data(), (const float*)d_subsig, sub_off.data(),
+                            B, K, max_offset_samples, o_score, o_offset, d_status, winner_only,
+                            fused ? &cue_src : nullptr));
+    B2_TRY(b2i_reduce_launch(h, o_score, o_offset, d_status, B, K, max_offset_samples, o_bs, o_bo, o_bk));
+  } else {
+    if (n_sub > b2_ctx::kEvents - 2) n_sub = b2_ctx::kEvents - 2;
+    std::vector<cudaEvent_t> vad_done(n_sub);
+    cudaEvent_t inputs_ready = next_event(h);
+    B2_CUDA(h, cudaEventRecord(inputs_ready, h->stream));
     {
       Stream2Scope on2(h);
-      B2_CUDA(h, cudaStreamWaitEvent(h->stream, vad_done, 0));
+      B2_CUDA(h, cudaStreamWaitEvent(h->stream, inputs_ready, 0));
+      for (int i = 0; i < n_sub; ++i) {
+        const int b0 = (int)((int64_t)B * i / n_sub), b1 = (int)((int64_t)B * (i + 1) / n_sub);
+        h->vad_partition_sms = i > 0 ? vad_sms : 0;
+        const int st = b1 > b0 ? b2i_vad_launch(h, d_pcm, pcm_off + b0, b1 - b0, fpw, non_speech_label,
+                                                (int64_t)fpw * energy_threshold, z_lo, z_hi, (float*)d_refsig,
+                                                ref_off.data() + b0)
+                               : B2_OK;
+        h->vad_partition_sms = 0;
+        if (st != B2_OK) return st;
+        vad_done[i] = next_event(h);
+        B2_CUDA(h, cudaEventRecord(vad_done[i], h->stream));
+      }
+    }
+    for (int i = 0; i < n_sub; ++i) {
+      const int b0 = (int)((int64_t)B * i / n_sub), b1 = (int)((int64_t)B * (i + 1) / n_sub);
+      const int nb = b1 - b0;
+      B2_CUDA(h, cudaStreamWaitEvent(h->stream, vad_done[i], 0));
+      if (nb == 0) continue;
       const size_t j0 = (size_t)b0 * K;
       if (!fused)
-        B2_TRY(b2i_raster_launch(h, cue_start_s, cue_end_s, cue_keep, cue_off + b0, nb, ratios, K, 0,
-                                 nullptr, sample_rate, start_seconds, (float*)d_subsig,
-                                 sub_off.data() + j0));
+        B2_TRY(b2i_raster_launch(h, cue_start_s, cue_end_s, cue_keep, cue_off + b0, nb, ratios, K, 0, nullptr,
+                                 sample_rate, start_seconds, (float*)d_subsig, sub_off.data() + j0));
       B2CueSource sub_src = cue_src;
       sub_src.cue_off = cue_off + b0;
       B2_TRY(b2i_align_launch(h, (const float*)d_refsig, ref_off.data() + b0, (const float*)d_subsig,
-                              sub_off.data() + j0, nb, K, max_offset_samples, o_score + j0,
-                              o_offset + j0, d_status + j0, winner_only, fused ? &sub_src : nullptr));
-      B2_TRY(b2i_reduce_launch(h, o_score + j0, o_offset + j0, d_status + j0, nb, K,
-                               max_offset_samples, o_bs + b0, o_bo + b0, o_bk + b0));
-      done2 = next_event(h);
-      B2_CUDA(h, cudaEventRecord(done2, h->stream));
+                              sub_off.data() + j0, nb, K, max_offset_samples, o_score + j0, o_offset + j0,
+                              d_status + j0, winner_only, fused ? &sub_src : nullptr));
+      B2_TRY(b2i_reduce_launch(h, o_score + j0, o_offset + j0, d_status + j0, nb, K, max_offset_samples,
+                               o_bs + b0, o_bo + b0, o_bk + b0));
     }
   }
-  if (done2) B2_CUDA(h, cudaStreamWaitEvent(h->stream, done2, 0));  // caller's stream sees everything
   if (memspace == B2_DEVICE) return B2_OK;
   B2_TRY(copy_out(h, best_score, d_bs, (size_t)B * 8));
   B2_TRY(copy_out(h, best_offset, d_bo, (size_t)B * 4));

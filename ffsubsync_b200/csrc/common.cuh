@@ -90,7 +90,7 @@ struct b2_ctx {
     cudaEvent_t ev = nullptr;
   } bounce[2];
   cudaStream_t stream2 = nullptr;
-  static const int kEvents = 16;
+  static const int kEvents = 64;
   cudaEvent_t ev_pool[kEvents] = {};
   int ev_next = 0;
 };
@@ -146,6 +146,7 @@ static inline int64_t ceil_div64(int64_t a, int64_t b) { return (a + b - 1) / b;
 // e_min_full: smallest sum of squares of a full window that is speech.  tail_emin_host (nullable,
 // [B]): evaluate each signal's trailing partial window against its own floor (auditok contract);
 // null = partial windows are non-speech (webrtc contract).
+bool b2i_vad_lane_eligible(const int64_t* pcm_off_host, int B, int fpw);
 int b2i_vad_launch(b2_ctx* h, const int16_t* d_pcm, const int64_t* pcm_off_host, int B, int fpw,
                    float non_speech_label, int64_t e_min_full, int z_lo, int z_hi,
                    float* d_out, const int64_t* out_off_host, const int64_t* tail_emin_host = nullptr);

@@ -15,6 +15,7 @@
 // straight out of shared memory (conflict-free LDS.128) and release the stage through its
 // "empty" mbarrier - no CTA-wide barrier on the steady-state path.
 #include "common.cuh"
+#include "vad_lane.cuh"
 
 namespace {
 
@@ -22,6 +23,13 @@ namespace {
 // (one CTA per SM with a ring of up to 10 stages: the SM-partitioned launch that shares the GPU
 // with the correlation kernels, b2_sync_batch pipeline)
 constexpr int kMaxStages = 10;
+// lane-per-window kernel (vad_lane.cuh): tiles of 32 windows per consumer WARP, in a ring of up to
+// kLaneMaxStages stages that fills the SM's shared memory; the producer warp claims and stages kLaneBatch
+// tiles at a time, one per lane
+constexpr int kLaneMaxStages = 24;
+constexpr int kLaneBatch = 5;
+constexpr int kLaneConsumers = 256;
+constexpr int kLanePipes = 2;
 
 struct TileDesc {
   long long out_base;   // index into out[] of the tile's first window
@@ -32,6 +40,7 @@ struct TileDesc {
   int head_bytes;       // offset of the first sample inside the 16 B-aligned staged span
   int tail_src_off;     // >=0: bytes [tail_src_off, tail_end) of the span must be copied by hand
   int tail_end;
+  int seq;              // lane-per-window kernel: number of the tile in its CTA's staging order
 };
 
 struct VadParams {
@@ -48,7 +57,7 @@ struct VadParams {
   // samples it has, speech <=> sum x^2 >= tail_emin[b] (no zero-crossing band).  nullptr: the
   // webrtc contract - a partial window is non-speech.
   const long long* tail_emin;
-  int B, fpw, G, tw, z_lo, z_hi, fast, stage_bytes, cpl, stages, consumers;
+  int B, fpw, G, tw, z_lo, z_hi, fast, stage_bytes, cpl, stages, consumers, batch, evict_first;
   float label;
 };
 
@@ -194,6 +203,49 @@ __device__ __forceinline__ void consume_tile_fast(const VadParams& p, const Tile
   }
 }
 
+// Descriptor of tile t (cur_b: signal index carried by the caller, tiles are claimed in ascending order);
+// bulk = bytes the 1-D bulk copy moves from p.pcm_bytes + d.span_gbyte.
+__device__ __forceinline__ TileDesc make_tile(const VadParams& p, long long t, int& cur_b, uint32_t& bulk) {
+  TileDesc d;
+  while (t >= p.tile_off[cur_b + 1]) ++cur_b;
+  const long long w0 = (t - p.tile_off[cur_b]) * p.tw;
+  const long long sig0 = p.pcm_off[cur_b], sig1 = p.pcm_off[cur_b + 1];
+  const long long nwin = p.out_off[cur_b + 1] - p.out_off[cur_b];
+  const int nw = (int)min((long long)p.tw, nwin - w0);
+  const long long s0 = sig0 + w0 * p.fpw;
+  const long long s1 = min(s0 + (long long)nw * p.fpw, sig1);
+  const long long b0 = 2 * s0, b1 = 2 * s1;
+  const long long a0 = b0 & ~15LL;
+  const long long a1 = (b1 + 15) & ~15LL;
+  const long long limit = p.pcm_total_bytes & ~15LL;  // bulk copies stay inside the buffer
+  const long long bulk_end = min(a1, limit);
+  bulk = bulk_end > a0 ? (uint32_t)(bulk_end - a0) : 0u;
+  d.n_windows = nw;
+  d.sig = cur_b;
+  d.out_base = p.out_off[cur_b] + w0;
+  d.n_left = sig1 - s0;
+  d.head_bytes = (int)(b0 - a0);
+  d.span_gbyte = a0;
+  if (bulk_end < b1) {  // ragged end of the whole buffer: < 16 bytes copied by hand
+    d.tail_src_off = (int)(max(bulk_end, a0) - a0);
+    d.tail_end = (int)(b1 - a0);
+  } else {
+    d.tail_src_off = -1;
+    d.tail_end = 0;
+  }
+  return d;
+}
+__device__ __forceinline__ TileDesc end_tile() {
+  TileDesc d;
+  d.n_windows = 0;
+  d.sig = 0;
+  d.out_base = d.n_left = d.span_gbyte = 0;
+  d.head_bytes = 0;
+  d.tail_src_off = -1;
+  d.tail_end = 0;
+  return d;
+}
+
 template <int kConsumerThreads>
 __global__ void __launch_bounds__(kConsumerThreads + 32) vad_energy_zcr_kernel(VadParams p) {
   extern __shared__ __align__(128) unsigned char smem[];
@@ -229,46 +281,16 @@ __global__ void __launch_bounds__(kConsumerThreads + 32) vad_energy_zcr_kernel(V
       const long long t = (long long)atomicAdd(p.tile_counter, 1ULL);
       TileDesc d;
       if (t >= p.total_tiles) {
-        d.n_windows = 0;
-        d.sig = 0;
-        d.out_base = d.n_left = d.span_gbyte = 0;
-        d.head_bytes = 0;
-        d.tail_src_off = -1;
-        d.tail_end = 0;
-        descs[stage] = d;
+        descs[stage] = end_tile();
         mbar_arrive(&full_bar[stage]);
         return;
       }
-      while (t >= p.tile_off[cur_b + 1]) ++cur_b;
-      const long long w0 = (t - p.tile_off[cur_b]) * p.tw;
-      const long long sig0 = p.pcm_off[cur_b], sig1 = p.pcm_off[cur_b + 1];
-      const long long nwin = p.out_off[cur_b + 1] - p.out_off[cur_b];
-      const int nw = (int)min((long long)p.tw, nwin - w0);
-      const long long s0 = sig0 + w0 * p.fpw;
-      const long long s1 = min(s0 + (long long)nw * p.fpw, sig1);
-      const long long b0 = 2 * s0, b1 = 2 * s1;
-      const long long a0 = b0 & ~15LL;
-      const long long a1 = (b1 + 15) & ~15LL;
-      const long long limit = p.pcm_total_bytes & ~15LL;  // bulk copies stay inside the buffer
-      const long long bulk_end = min(a1, limit);
-      const uint32_t bulk = bulk_end > a0 ? (uint32_t)(bulk_end - a0) : 0u;
-      d.n_windows = nw;
-      d.sig = cur_b;
-      d.out_base = p.out_off[cur_b] + w0;
-      d.n_left = sig1 - s0;
-      d.head_bytes = (int)(b0 - a0);
-      d.span_gbyte = a0;
-      if (bulk_end < b1) {  // ragged end of the whole buffer: < 16 bytes copied by hand
-        d.tail_src_off = (int)(max(bulk_end, a0) - a0);
-        d.tail_end = (int)(b1 - a0);
-      } else {
-        d.tail_src_off = -1;
-        d.tail_end = 0;
-      }
+      uint32_t bulk;
+      d = make_tile(p, t, cur_b, bulk);
       descs[stage] = d;
       if (bulk) {
         mbar_arrive_expect_tx(&full_bar[stage], bulk);
-        tma_bulk_g2s(data + (size_t)stage * p.stage_bytes, p.pcm_bytes + a0, bulk, &full_bar[stage]);
+        tma_bulk_g2s(data + (size_t)stage * p.stage_bytes, p.pcm_bytes + d.span_gbyte, bulk, &full_bar[stage]);
       } else {
         mbar_arrive(&full_bar[stage]);
       }
@@ -332,6 +354,243 @@ __global__ void __launch_bounds__(kConsumerThreads + 32) vad_energy_zcr_kernel(V
   }
 }
 
+// Bulk copy with an L2 evict-first policy: the PCM is read once; keeping it from displacing the reference
+// spectra that the correlation kernels on the other SMs re-read K times (SM-partitioned pipeline).
+__device__ __forceinline__ void tma_bulk_g2s_stream(void* dst, const void* src, uint32_t bytes, uint64_t* bar,
+                                                    uint64_t policy) {
+  asm volatile(
+      "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;" ::
+          "r"(smem_u32(dst)),
+      "l"(src), "r"(bytes), "r"(smem_u32(bar)), "l"(policy)
+      : "memory");
+}
+__device__ __forceinline__ uint64_t l2_evict_first_policy() {
+  uint64_t pol;
+  asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
+  return pol;
+}
+
+// ---- lane-per-window kernel ---------------------------------------------------------------------
+// Same contract as above; tiles of 32 * WPL windows, tile number q of a CTA (in the order its producer
+// stages them) goes to ring stage q mod nst and to consumer warp q mod 8; lane i of the warp reduces
+// windows i, i + 32, ... with vadlane::lane_window (17 instructions per 16 bytes, no shuffles): 1.3
+// instructions per byte and lane against 3.25 for the lane-group layout.  Launched for 8 and 16 kHz
+// (C = 10, 20 chunks per window) and 16-byte aligned signals; everything else takes the kernel above.
+//
+// Producer.  One warp per SM has to stage a 10 KB tile every ~200 cycles to feed 100 GB/s per SM; a single
+// thread needs ~600 (measured: 27-32 GB/s per SM).  So: the signal's table entries stay in registers
+// (reloaded when a lane's tile sequence crosses into the next signal), interior tiles take a 20-instruction
+// descriptor path, kLaneBatch lanes stage kLaneBatch tiles side by side (wait for the stage, descriptor,
+// expect-tx, bulk copy: one pass of the instruction stream), and the next claim is requested one batch ahead.
+//
+// Consumers.  Bulk copies complete out of order, and a parity wait cannot tell "phase r complete" from
+// "phase r - 2 complete": a warp that waits for tile q while the previous user of the stage (tile q - nst,
+// consumed by a DIFFERENT warp) is still in flight would sail through.  The descriptor therefore carries the
+// tile's sequence number: the producer writes it after the stage was released and before it arms the barrier,
+// the consumer first polls it, then waits on the barrier (now at most one phase behind).
+struct SigCache {
+  int b;                    // signal index, -1 = nothing loaded
+  long long tile_lo, tile_hi, sig0, sig1, nwin, out0;
+};
+__device__ __forceinline__ TileDesc make_tile_cached(const VadParams& p, long long t, SigCache& c, uint32_t& bulk) {
+  if (c.b < 0 || t >= c.tile_hi) {
+    int b = c.b < 0 ? 0 : c.b;
+    while (t >= p.tile_off[b + 1]) ++b;
+    c.b = b;
+    c.tile_lo = p.tile_off[b];
+    c.tile_hi = p.tile_off[b + 1];
+    c.sig0 = p.pcm_off[b];
+    c.sig1 = p.pcm_off[b + 1];
+    c.out0 = p.out_off[b];
+    c.nwin = p.out_off[b + 1] - c.out0;
+  }
+  TileDesc d;
+  const long long w0 = (t - c.tile_lo) * p.tw;
+  const long long s0 = c.sig0 + w0 * p.fpw;
+  d.sig = c.b;
+  d.out_base = c.out0 + w0;
+  d.n_left = c.sig1 - s0;
+  d.seq = 0;
+  if (t + 1 < c.tile_hi) {
+    // interior tile of a 16-byte aligned signal: whole windows, aligned at both ends, inside the buffer
+    d.n_windows = p.tw;
+    d.head_bytes = 0;
+    d.span_gbyte = 2 * s0;
+    d.tail_src_off = -1;
+    d.tail_end = 0;
+    bulk = (uint32_t)(p.tw * p.fpw * 2);
+    return d;
+  }
+  const int nw = (int)min((long long)p.tw, c.nwin - w0);
+  const long long s1 = min(s0 + (long long)nw * p.fpw, c.sig1);
+  const long long b0 = 2 * s0, b1 = 2 * s1;
+  const long long a0 = b0 & ~15LL;
+  const long long a1 = (b1 + 15) & ~15LL;
+  const long long limit = p.pcm_total_bytes & ~15LL;  // bulk copies stay inside the buffer
+  const long long bulk_end = min(a1, limit);
+  bulk = bulk_end > a0 ? (uint32_t)(bulk_end - a0) : 0u;
+  d.n_windows = nw;
+  d.head_bytes = (int)(b0 - a0);
+  d.span_gbyte = a0;
+  if (bulk_end < b1) {  // ragged end of the whole buffer: < 16 bytes copied by hand
+    d.tail_src_off = (int)(max(bulk_end, a0) - a0);
+    d.tail_end = (int)(b1 - a0);
+  } else {
+    d.tail_src_off = -1;
+    d.tail_end = 0;
+  }
+  return d;
+}
+
+// Tile claim.  ptxas turns an atomic add on a provably uniform address into a warp-aggregated atomic whose
+// result is shuffled out right away: the full round trip to L2 (~1300 cycles under load) then sits in front
+// of every batch (measured: 1300 cycles + 140 per tile, for every batch size).  `skew` is a per-lane zero
+// read from shared memory: the address is no longer provably uniform, the atomic stays a plain one and
+// returns through the scoreboard - the warp stalls only where the value is used, one batch later.
+__device__ __forceinline__ long long claim_tiles(unsigned long long* counter, int n, int skew) {
+  unsigned long long r;
+  asm volatile("atom.global.add.u64 %0, [%1], %2;" : "=l"(r) : "l"(counter + skew), "l"((unsigned long long)n) : "memory");
+  return (long long)r;
+}
+
+template <int C, int WPL>
+__global__ void __launch_bounds__(kLaneConsumers + 32 * kLanePipes) vad_lane_kernel(VadParams p) {
+  constexpr int RMAX = vadlane::rotation_max(C);
+  // kLanePipes independent pipelines per CTA: a producer warp, kLaneConsumers / 32 / kLanePipes consumer
+  // warps and p.stages ring stages each (the producer's instruction stream is latency-bound: ~1200 cycles per
+  // batch whatever the batch holds - two of them stage twice as much)
+  constexpr int kWarps = kLaneConsumers / 32 / kLanePipes;   // consumer warps per pipeline
+  extern __shared__ __align__(128) unsigned char smem[];
+  const int nst = p.stages;   // per pipeline
+  const int tid = threadIdx.x;
+  const int warp = tid >> 5;
+  const bool is_producer = tid >= kLaneConsumers;
+  const int pipe = is_producer ? warp - kLaneConsumers / 32 : warp / kWarps;
+  uint64_t* bar0 = reinterpret_cast<uint64_t*>(smem + (size_t)kLanePipes * nst * p.stage_bytes);
+  TileDesc* desc0 = reinterpret_cast<TileDesc*>(bar0 + 2 * kLaneMaxStages);
+  unsigned char* data = smem + (size_t)pipe * nst * p.stage_bytes;
+  uint64_t* full_bar = bar0 + pipe * nst;
+  uint64_t* empty_bar = bar0 + kLaneMaxStages + pipe * nst;
+  TileDesc* descs = desc0 + pipe * nst;
+  volatile int* zeros = reinterpret_cast<volatile int*>(desc0 + kLaneMaxStages);   // 64 spare bytes
+  if (tid == 0) {
+    for (int s = 0; s < kLaneMaxStages; ++s) {
+      mbar_init(&bar0[s], 1);
+      mbar_init(&bar0[kLaneMaxStages + s], 1);   // released by the one warp that consumed the stage
+      desc0[s].seq = -1;
+    }
+    for (int i = 0; i < 8; ++i) zeros[i] = 0;   // claim_tiles' skew
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+
+  if (is_producer) {
+    // ================================ producer warp ==========================================
+    const int lane = tid & 31;
+    SigCache sc;
+    sc.b = -1;
+    int q0 = 0;              // sequence number of the batch's first tile; it lives in stage0, ring pass `round`
+    int stage0 = 0;
+    uint32_t round = 0;
+    int ends_left = kWarps;  // end markers still to post once the tiles are gone: one per consumer warp
+    long long pending = 0;   // lane 0: first tile of the next claim, requested one batch ahead
+    const int skew = zeros[lane & 7];   // 0, opaque to ptxas
+    const uint64_t l2_policy = l2_evict_first_policy();
+    if (lane == 0) pending = claim_tiles(p.tile_counter, p.batch, skew);
+    for (;;) {
+      const long long t0 = __shfl_sync(0xffffffffu, pending, 0);
+      const int n = (int)max(0LL, min((long long)p.batch, p.total_tiles - t0));
+      if (n > 0 && lane == 0) pending = claim_tiles(p.tile_counter, p.batch, skew);
+      const int count = n > 0 ? n : min(ends_left, p.batch);   // slots staged by this batch
+      if (lane < count) {
+        TileDesc d = end_tile();
+        uint32_t bulk = 0;
+        if (n > 0) d = make_tile_cached(p, t0 + lane, sc, bulk);
+        d.seq = q0 + lane;
+        int stage = stage0 + lane;
+        uint32_t rnd = round;
+        if (stage >= nst) {
+          stage -= nst;
+          ++rnd;
+        }
+        if (rnd > 0) mbar_wait(&empty_bar[stage], (rnd - 1) & 1u);
+        descs[stage] = d;
+        if (bulk) {
+          mbar_arrive_expect_tx(&full_bar[stage], bulk);
+          if (p.evict_first)
+            tma_bulk_g2s_stream(data + (size_t)stage * p.stage_bytes, p.pcm_bytes + d.span_gbyte, bulk,
+                                &full_bar[stage], l2_policy);
+          else
+            tma_bulk_g2s(data + (size_t)stage * p.stage_bytes, p.pcm_bytes + d.span_gbyte, bulk, &full_bar[stage]);
+        } else {
+          mbar_arrive(&full_bar[stage]);
+        }
+      }
+      __syncwarp();
+      q0 += count;
+      stage0 += count;
+      if (stage0 >= nst) {
+        stage0 -= nst;
+        ++round;
+      }
+      if (n == 0) {
+        ends_left -= count;
+        if (ends_left == 0) return;
+      }
+    }
+  }
+
+  // ================================== consumer warps ==========================================
+  const int lane = tid & 31;
+  const int rot = vadlane::lane_rotation(C, lane);
+  constexpr int fpw = 8 * C;
+  int q = warp - pipe * kWarps;      // this warp's first tile
+  int stage = q;                     // nst >= kWarps (launch condition)
+  uint32_t phase = 0;
+  for (;;) {
+    // tile q staged?  (see above: only then is the parity wait unambiguous)
+    while (*reinterpret_cast<volatile int*>(&descs[stage].seq) != q) {
+    }
+    mbar_wait(&full_bar[stage], phase);
+    const TileDesc d = descs[stage];
+    if (d.n_windows == 0) break;
+    unsigned char* span = data + (size_t)stage * p.stage_bytes;
+    if (d.tail_src_off >= 0) {  // rare: last < 16 bytes of the whole PCM buffer
+      const int nb = d.tail_end - d.tail_src_off;
+      if (lane < nb) span[d.tail_src_off + lane] = p.pcm_bytes[d.span_gbyte + d.tail_src_off + lane];
+      __syncwarp();
+    }
+#pragma unroll 1
+    for (int k = 0; k < WPL; ++k) {
+      const int wl = lane + 32 * k;
+      const bool active = wl < d.n_windows;
+      const long long avail = d.n_left - (long long)wl * fpw;
+      const bool full = active && avail >= fpw;
+      long long e = 0;
+      int z = 0;
+      bool speech = false;
+      if (full) {   // tiles start 16-byte aligned (launch condition): head_bytes == 0
+        vadlane::lane_window<C, RMAX>(span + (size_t)wl * (fpw * 2), rot, e, z);
+        speech = e >= p.e_min && z >= p.z_lo && z <= p.z_hi;
+      } else if (active && avail > 0 && p.tail_emin != nullptr) {
+        // auditok contract: the trailing partial window of a signal is judged on the samples it has
+        const short* xs = reinterpret_cast<const short*>(span + (size_t)wl * (fpw * 2));
+        for (int i = 0; i < (int)avail; ++i) e += (long long)xs[i] * xs[i];
+        speech = e >= p.tail_emin[d.sig];
+      }
+      if (active) p.out[d.out_base + wl] = speech ? 1.0f : p.label;
+    }
+    __syncwarp();
+    if (lane == 0) mbar_arrive(&empty_bar[stage]);
+    q += kWarps;
+    stage += kWarps;
+    if (stage >= nst) {
+      stage -= nst;
+      phase ^= 1u;
+    }
+  }
+}
+
 // ------------------------------------------------------------------------------ synthesiser
 __device__ __forceinline__ uint32_t lowbias32(uint32_t x) {
   x ^= x >> 16;
@@ -372,6 +631,17 @@ int b2i_synth_launch(b2_ctx* h, const uint8_t* d_cls, int64_t n_windows, int fpw
   synth_pcm_kernel<<<blocks, 256, 0, h->stream>>>(d_cls, n_windows, fpw, seed, (short*)d_out);
   B2_CHECK_LAUNCH(h, "synth_pcm_kernel");
   return B2_OK;
+}
+
+// Would b2i_vad_launch take the lane-per-window kernel for these signals?  (b2_sync_batch pipelines
+// sub-batches over an SM partition only then.)
+bool b2i_vad_lane_eligible(const int64_t* pcm_off, int B, int fpw) {
+  if (fpw != 80 && fpw != 160) return false;
+  if (const char* e = getenv("B2_VAD_LAYOUT"))
+    if (strcmp(e, "group") == 0) return false;
+  for (int b = 0; b < B; ++b)
+    if (pcm_off[b] % 8 != 0) return false;
+  return true;
 }
 
 int b2i_vad_launch(b2_ctx* h, const int16_t* d_pcm, const int64_t* pcm_off, int B, int fpw,
@@ -443,6 +713,33 @@ int b2i_vad_launch(b2_ctx* h, const int16_t* d_pcm, const int64_t* pcm_off, int 
     if (pcm_off[b] % 8 != 0) aligned = false;
   }
   if (!aligned) p.fast = 0;  // window starts are not 16-byte aligned in the staged span
+  // lane-per-window kernel: 16-byte aligned signals and an instantiated chunk count (8 / 16 / 32 / 48 kHz
+  // at 100 windows per second).  B2_VAD_LAYOUT=group keeps the lane-group kernel (A/B and test knob).
+  bool lane_layout = p.fast && (C == 10 || C == 20);
+  if (const char* e = getenv("B2_VAD_LAYOUT")) lane_layout = lane_layout && strcmp(e, "group") != 0;
+  // windows per lane and tile: stages of 10 KB
+  int wpl = C == 10 ? 2 : 1;
+  if (const char* e = getenv("B2_VAD_WPL")) wpl = (C == 10 ? 2 : 1) * (atoi(e) >= 2 ? 2 : 1);   // tuning knob
+  if (lane_layout) {
+    p.tw = 32 * wpl;
+    p.stage_bytes = ((p.tw * fpw * 2 + 32) + 127) & ~127;
+    // ring stages per pipeline (at least one per consumer warp of the pipeline)
+    stages = std::min<int>(kLaneMaxStages, (int)((208 * 1024) / p.stage_bytes)) / kLanePipes;
+    if (const char* e = getenv("B2_VAD_STAGES"))
+      stages = std::max(kLaneConsumers / 32 / kLanePipes, std::min(stages, atoi(e)));
+    p.consumers = kLaneConsumers;
+    p.stages = stages;
+    p.evict_first = 1;
+    if (const char* e = getenv("B2_VAD_EVICT_FIRST")) p.evict_first = atoi(e) != 0;   // A/B knob
+    p.batch = kLaneBatch;
+    if (const char* e = getenv("B2_VAD_BATCH")) p.batch = std::max(1, std::min(16, atoi(e)));   // tuning knob
+    smem = (size_t)kLanePipes * stages * p.stage_bytes + 2 * kLaneMaxStages * sizeof(uint64_t) +
+           kLaneMaxStages * sizeof(TileDesc) + 64;
+    for (int b = 0; b < B; ++b) {
+      const long long n = pcm_off[b + 1] - pcm_off[b];
+      tile_off[b + 1] = tile_off[b] + ((n + fpw - 1) / fpw + p.tw - 1) / p.tw;
+    }
+  }
   p.total_tiles = tile_off[B];
   if (p.total_tiles == 0) return B2_OK;
 
@@ -468,6 +765,19 @@ int b2i_vad_launch(b2_ctx* h, const int16_t* d_pcm, const int64_t* pcm_off, int 
   B2_TRY(b2i_ws(h, b2_ctx::WS_COUNTERS, 64, &d_counter));
   p.tile_counter = (unsigned long long*)d_counter;
   B2_CUDA(h, cudaMemsetAsync(d_counter, 0, 8, h->stream));
+  if (lane_layout) {
+    void (*lk)(VadParams) = C == 10 ? (wpl == 2 ? vad_lane_kernel<10, 2> : vad_lane_kernel<10, 4>)
+                                    : (wpl == 1 ? vad_lane_kernel<20, 1> : vad_lane_kernel<20, 2>);
+    if (smem < 116 * 1024) smem = 116 * 1024;   // one CTA per SM: the ring is sized for the whole SM
+    B2_CUDA(h, cudaFuncSetAttribute(lk, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    // tiles are claimed kLaneBatch at a time: no point in more CTAs than claims
+    long long grid = std::min<long long>((p.total_tiles + kLanePipes * p.batch - 1) / (kLanePipes * p.batch), (long long)h->sm_count);
+    if (h->vad_partition_sms > 0) grid = std::min<long long>(grid, h->vad_partition_sms);
+    if (const char* e = getenv("B2_VAD_GRID")) grid = std::max<long long>(1, std::min<long long>(grid, atoll(e)));
+    lk<<<(unsigned)grid, kLaneConsumers + 32 * kLanePipes, smem, h->stream>>>(p);
+    B2_CHECK_LAUNCH(h, "vad_lane_kernel");
+    return B2_OK;
+  }
   if (consumers == 512 && smem < 116 * 1024) smem = 116 * 1024;  // never two of these on one SM
   auto kernel = consumers == 512 ? vad_energy_zcr_kernel<512> : vad_energy_zcr_kernel<256>;
   B2_CUDA(h, cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));

@@ -473,3 +473,15 @@ def test_bigfft_roundoff_adversarial(built):
         got, es, er, cn = _emulate_big(ref, sub, 7, 0)
         want = _direct_big(ref, sub, 1 << 18)
         assert np.abs(got - want).max() <= _tau(es, er, cn) / 4, (fam_r, fam_s)
+
+
+# --------------------------------------------------------- CPU emulation of the lane-per-window VAD
+
+def test_vad_lane_arithmetic_emulation(built):
+    """csrc/vad_lane.cuh (byte dot products, circular chunk order) == sum x^2 / sign changes, for every
+    instantiated window size, every start chunk, int16 extremes; and the bank-group bijection."""
+    exe = os.path.join(ROOT, "tests", "host_emul", "vad_emul")
+    out = subprocess.run([exe, "140"], capture_output=True, text=True)
+    assert out.returncode == 0, out.stdout
+    assert out.stdout.startswith("ok "), out.stdout
+    assert int(out.stdout.split()[1]) > 50000
