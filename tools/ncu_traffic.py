@@ -1,5 +1,5 @@
 #!/usr/bin/env python
-"""DRAM traffic per launch of vad_energy_zcr_kernel from an `ncu --set full` capture ->
+"""DRAM traffic per launch of the VAD kernel (vad_lane_kernel or vad_energy_zcr_kernel) from an `ncu --set full` capture ->
 profiles/r2_vad_traffic.json (bench.py reads it for roofline.traffic instead of a hard-coded ratio).
 
     python tools/ncu_traffic.py gpurun_out/r2_vad.ncu-rep [pairs in the captured launch]
@@ -33,19 +33,19 @@ def main(path, pairs):
     dur = hdr.index("gpu__time_duration.sum")
     best = None
     for row in rows[2:]:
-        if "vad_energy_zcr_kernel" not in row[name]:
+        if "vad_lane_kernel" not in row[name] and "vad_energy_zcr_kernel" not in row[name]:
             continue
         traffic = to_bytes(row[rd], units[rd]) + to_bytes(row[wr], units[wr])
         if pairs <= 0:
             pairs = max(1, int(round(to_bytes(row[rd], units[rd]) / 230.4e6)))
         if best is None or traffic > best["dram_bytes_per_launch"]:
-            best = {"kernel": "vad_energy_zcr_kernel", "pairs": pairs,
+            best = {"kernel": row[name].split("(")[0], "pairs": pairs,
                     "dram_bytes_read": to_bytes(row[rd], units[rd]), "dram_bytes_write": to_bytes(row[wr], units[wr]),
                     "dram_bytes_per_launch": traffic, "algorithmic_bytes_per_launch": BYTES_VAD * pairs,
                     "duration_under_ncu": "%s %s" % (row[dur], units[dur]),
                     "source": "profiles/%s" % os.path.basename(path).replace(".ncu-rep", "_summary.txt")}
     if best is None:
-        raise SystemExit("no vad_energy_zcr_kernel launch in %s" % path)
+        raise SystemExit("no VAD kernel launch in %s" % path)
     best["ratio"] = best["dram_bytes_per_launch"] / best["algorithmic_bytes_per_launch"]
     out = os.path.join(ROOT, "profiles", "r2_vad_traffic.json")
     with open(out, "w") as fh:

@@ -37,6 +37,19 @@ def main():
         pcm = vo.synth_pcm(rng.randint(0, 3, 700).astype(np.uint8), fpw, seed=3)[: 700 * fpw - 5]
         got, _ = h.vad_energy_zcr(pcm, [0, len(pcm)], fr, 100, 0.0, 100000)
         assert np.array_equal(got.astype(np.float64), vo.energy_zcr_detect(pcm, 100, fr, 0.0)), fr
+    # lane-per-window kernel (16 kHz and 8 kHz, aligned multi-signal batch, ragged last window) against the
+    # lane-group kernel on the same input, then in its SM-partitioned shape (grid capped)
+    for fr in (16000, 8000):
+        fpw = vo.frames_per_window(fr, 100)
+        pcm = vo.synth_pcm(rng.randint(0, 3, 2600).astype(np.uint8), fpw, seed=5)[: 2600 * fpw - 3]
+        offs = [0, fpw * 1000, fpw * 1800, len(pcm)]
+        want = np.concatenate([vo.energy_zcr_detect(pcm[a:b], 100, fr, 0.0) for a, b in zip(offs[:-1], offs[1:])])
+        for env in ({}, {"B2_VAD_LAYOUT": "group"}, {"B2_VAD_GRID": "3"}, {"B2_VAD_BATCH": "2", "B2_VAD_STAGES": "4"}):
+            os.environ.update(env)
+            got, _ = h.vad_energy_zcr(pcm, offs, fr, 100, 0.0, 100000)
+            for k in env:
+                os.environ.pop(k)
+            assert np.array_equal(got.astype(np.float64), want), (fr, env)
     os.environ.update(B2_VAD_CONSUMERS="512", B2_VAD_CTAS_FORCE="1", B2_VAD_GRID="5")
     pcm = vo.synth_pcm(rng.randint(0, 3, 3000).astype(np.uint8), 160, seed=4)
     got, _ = h.vad_energy_zcr(pcm, [0, 160 * 1000, len(pcm)], 16000, 100, 0.0, 100000)
@@ -78,10 +91,12 @@ def main():
     args = (pcm, [0, n_win * 160, 2 * n_win * 160], np.tile(starts, 2), np.tile(ends, 2), cue_off)
     base = bs.sync_host(*args)
     assert list(base[1]) == [200, 200] and list(base[2]) == [0, 0], base
-    os.environ["B2_SUBBATCHES"] = "2"
-    piped = bs.sync_host(*args)
-    os.environ.pop("B2_SUBBATCHES")
-    assert all(np.array_equal(a, b) for a, b in zip(base, piped))
+    for env in ({"B2_SUBBATCHES": "2"}, {"B2_SUBBATCHES": "2", "B2_VAD_SMS": "2"}):
+        os.environ.update(env)   # sub-batch pipeline: VAD on the internal stream, later sub-batches on B2_VAD_SMS SMs
+        piped = bs.sync_host(*args)
+        for k in env:
+            os.environ.pop(k)
+        assert all(np.array_equal(a, b) for a, b in zip(base, piped)), env
     h.synchronize()
     print("sanitize_smoke ok")
 
