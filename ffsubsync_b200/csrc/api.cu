@@ -4,6 +4,7 @@
 // on the CPU.
 #include <math.h>
 
+#include <chrono>
 #include <algorithm>
 #include <atomic>
 #include <thread>
@@ -953,6 +954,11 @@ extern "C" int b2_sync_batch(b2_handle h, const int16_t* pcm, const int64_t* pcm
   }
   if (const char* e = getenv("B2_SUBBATCHES")) n_sub = std::max(1, std::min(B, atoi(e)));
   if (const char* e = getenv("B2_VAD_SMS")) vad_sms = std::max(0, std::min(h->sm_count, atoi(e)));
+  // probe knobs (tools/pipeline_probe.py): share of the pairs in the first sub-batch (its VAD has nothing to
+  // overlap with; 0 = even split), and a cap on the persistent correlation grid while a VAD holds vad_sms SMs
+  int head_pct = 0, corr_cap = 0;
+  if (const char* e = getenv("B2_PIPE_HEAD_PCT")) head_pct = std::max(0, std::min(90, atoi(e)));
+  if (const char* e = getenv("B2_PIPE_CORR_CAP")) corr_cap = atoi(e) != 0;
   if (n_sub == 1) {
     B2_TRY(b2i_vad_launch(h, d_pcm, pcm_off, B, fpw, non_speech_label, (int64_t)fpw * energy_threshold, z_lo,
                           z_hi, (float*)d_refsig, ref_off.data()));
@@ -965,15 +971,46 @@ extern "C" int b2_sync_batch(b2_handle h, const int16_t* pcm, const int64_t* pcm
     B2_TRY(b2i_reduce_launch(h, o_score, o_offset, d_status, B, K, max_offset_samples, o_bs, o_bo, o_bk));
   } else {
     if (n_sub > b2_ctx::kEvents - 2) n_sub = b2_ctx::kEvents - 2;
+    std::vector<int> cut(n_sub + 1);
+    for (int i = 0; i <= n_sub; ++i) cut[i] = (int)((int64_t)B * i / n_sub);
+    if (head_pct > 0 && n_sub > 1) {
+      const int head = std::max(1, std::min(B - (n_sub - 1), (int)((int64_t)B * head_pct / 100)));
+      for (int i = 1; i <= n_sub; ++i) cut[i] = head + (int)((int64_t)(B - head) * (i - 1) / (n_sub - 1));
+    }
+    if (const char* e = getenv("B2_PIPE_CUTS")) {   // probe knob: explicit first pairs of sub-batches 1.., e.g. "54,135,197"
+      std::vector<int> c{0};
+      for (const char* q = e; *q;) {
+        char* end = nullptr;
+        const long v = strtol(q, &end, 10);
+        if (end == q) break;
+        if (v > c.back() && v < B && (int)c.size() < b2_ctx::kEvents - 2) c.push_back((int)v);
+        q = *end ? end + 1 : end;
+      }
+      c.push_back(B);
+      cut = c;
+      n_sub = (int)cut.size() - 1;
+    }
     std::vector<cudaEvent_t> vad_done(n_sub);
     cudaEvent_t inputs_ready = next_event(h);
     B2_CUDA(h, cudaEventRecord(inputs_ready, h->stream));
+    // B2_PIPE_TRACE=1 (diagnostic; synchronises): device timeline of the sub-batches and host enqueue times
+    const bool trace = getenv("B2_PIPE_TRACE") != nullptr;
+    std::vector<cudaEvent_t> tev;   // t0, then per sub-batch: VAD start, VAD end, chain start, chain end
+    std::vector<double> host_ms(n_sub + 1, 0.0);
+    const auto host_t0 = std::chrono::steady_clock::now();
+    auto host_now = [&]() { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - host_t0).count(); };
+    if (trace) {
+      tev.resize(1 + 4 * (size_t)n_sub);
+      for (auto& e : tev) B2_CUDA(h, cudaEventCreate(&e));
+      B2_CUDA(h, cudaEventRecord(tev[0], h->stream));
+    }
     {
       Stream2Scope on2(h);
       B2_CUDA(h, cudaStreamWaitEvent(h->stream, inputs_ready, 0));
       for (int i = 0; i < n_sub; ++i) {
-        const int b0 = (int)((int64_t)B * i / n_sub), b1 = (int)((int64_t)B * (i + 1) / n_sub);
+        const int b0 = cut[i], b1 = cut[i + 1];
         h->vad_partition_sms = i > 0 ? vad_sms : 0;
+        if (trace) B2_CUDA(h, cudaEventRecord(tev[1 + 4 * i], h->stream));
         const int st = b1 > b0 ? b2i_vad_launch(h, d_pcm, pcm_off + b0, b1 - b0, fpw, non_speech_label,
                                                 (int64_t)fpw * energy_threshold, z_lo, z_hi, (float*)d_refsig,
                                                 ref_off.data() + b0)
@@ -982,13 +1019,25 @@ extern "C" int b2_sync_batch(b2_handle h, const int16_t* pcm, const int64_t* pcm
         if (st != B2_OK) return st;
         vad_done[i] = next_event(h);
         B2_CUDA(h, cudaEventRecord(vad_done[i], h->stream));
+        if (trace) B2_CUDA(h, cudaEventRecord(tev[2 + 4 * i], h->stream));
       }
     }
+    host_ms[0] = host_now();
     for (int i = 0; i < n_sub; ++i) {
-      const int b0 = (int)((int64_t)B * i / n_sub), b1 = (int)((int64_t)B * (i + 1) / n_sub);
+      const int b0 = cut[i], b1 = cut[i + 1];
       const int nb = b1 - b0;
       B2_CUDA(h, cudaStreamWaitEvent(h->stream, vad_done[i], 0));
-      if (nb == 0) continue;
+      if (trace) B2_CUDA(h, cudaEventRecord(tev[3 + 4 * i], h->stream));
+      if (nb == 0) {
+        if (trace) B2_CUDA(h, cudaEventRecord(tev[4 + 4 * i], h->stream));
+        continue;
+      }
+      struct CapScope {   // restores the handle's grid cap on every exit path
+        b2_ctx* h;
+        int saved;
+        ~CapScope() { h->corr_max_ctas = saved; }
+      } cap_scope{h, h->corr_max_ctas};
+      if (corr_cap && i + 1 < n_sub && vad_sms > 0 && vad_sms < h->sm_count) h->corr_max_ctas = h->sm_count - vad_sms;
       const size_t j0 = (size_t)b0 * K;
       if (!fused)
         B2_TRY(b2i_raster_launch(h, cue_start_s, cue_end_s, cue_keep, cue_off + b0, nb, ratios, K, 0, nullptr,
@@ -1000,6 +1049,23 @@ extern "C" int b2_sync_batch(b2_handle h, const int16_t* pcm, const int64_t* pcm
                               d_status + j0, winner_only, fused ? &sub_src : nullptr));
       B2_TRY(b2i_reduce_launch(h, o_score + j0, o_offset + j0, d_status + j0, nb, K, max_offset_samples,
                                o_bs + b0, o_bo + b0, o_bk + b0));
+      if (trace) B2_CUDA(h, cudaEventRecord(tev[4 + 4 * i], h->stream));
+      host_ms[i + 1] = host_now();
+    }
+    if (trace) {
+      B2_CUDA(h, cudaStreamSynchronize(h->stream2));
+      B2_CUDA(h, cudaStreamSynchronize(h->stream));
+      auto at = [&](size_t k) {
+        float ms = 0.f;
+        cudaEventElapsedTime(&ms, tev[0], tev[k]);
+        return ms;
+      };
+      fprintf(stderr, "[b2 pipe] B=%d n_sub=%d vad_sms=%d head_pct=%d corr_cap=%d; host: VADs enqueued at %.3f ms\n", B, n_sub,
+              vad_sms, head_pct, corr_cap, host_ms[0]);
+      for (int i = 0; i < n_sub; ++i)
+        fprintf(stderr, "[b2 pipe]  sub %d pairs %4d..%4d  VAD %7.3f -> %7.3f ms   chain %7.3f -> %7.3f ms   host enqueued chain at %.3f ms\n",
+                i, cut[i], cut[i + 1], at(1 + 4 * i), at(2 + 4 * i), at(3 + 4 * i), at(4 + 4 * i), host_ms[i + 1]);
+      for (auto& e : tev) cudaEventDestroy(e);
     }
   }
   if (memspace == B2_DEVICE) return B2_OK;
