@@ -14,6 +14,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "_lib", "libffsubsync_b200.so")
 
 B2_HOST, B2_DEVICE = 0, 1
+B2_DEVICE_RESIDENT = 2   # b2_sync_batch only: device inputs that nothing queued before the call still writes
 B2_MAX_OFFSET_NONE = -(1 << 63)   # INT64_MIN: FFTAligner(max_offset_samples=None)
 ALIGN_OK, ALIGN_EMPTY, ALIGN_ALL_MASKED, ALIGN_CAND_OVERFLOW = 0, 1, 2, 4
 STATUS_NAMES = {0: "B2_OK", -1: "B2_ERR_BAD_ARG", -2: "B2_ERR_CUDA", -3: "B2_ERR_EMPTY_INPUT",

@@ -52,10 +52,15 @@ class BatchSynchronizer:
         import torch
         self.handle.set_stream(torch.cuda.current_stream().cuda_stream)
 
-    def sync_device(self, pcm, pcm_off, cue_start, cue_end, cue_off, cue_keep=None, out=None, all_out=None):
+    def sync_device(self, pcm, pcm_off, cue_start, cue_end, cue_off, cue_keep=None, out=None, all_out=None,
+                    inputs_resident: bool = False):
         """pcm: int16 CUDA tensor with all pairs back to back; pcm_off: [B+1] sample offsets (host).
         out: optional dict of preallocated CUDA tensors best_score f64[B], best_offset i32[B],
-        best_k i32[B].  Returns that dict; nothing is synchronised."""
+        best_k i32[B].  Returns that dict; nothing is synchronised.
+        inputs_resident=True (B2_DEVICE_RESIDENT): the caller promises that nothing queued on the handle's
+        stream before this call still writes ``pcm`` (a corpus that sits in HBM).  Back-to-back calls then
+        overlap: the VAD of this batch starts while the last correlation chain of the previous batch is
+        still running.  Results are identical; outputs stay ordered on the stream."""
         import torch
         B = len(pcm_off) - 1
         K = len(self.ratios)
@@ -70,7 +75,8 @@ class BatchSynchronizer:
             pcm.data_ptr(), pcm_off, self.frame_rate, self.sample_rate, self.non_speech_label,
             self.energy_threshold, self.z_lo, self.z_hi, cue_start, cue_end, cue_keep, cue_off, self.ratios,
             self.start_seconds, self.max_offset_samples, out["best_score"].data_ptr(),
-            out["best_offset"].data_ptr(), out["best_k"].data_ptr(), a_s, a_o, memspace=_native.B2_DEVICE)
+            out["best_offset"].data_ptr(), out["best_k"].data_ptr(), a_s, a_o,
+            memspace=_native.B2_DEVICE_RESIDENT if inputs_resident else _native.B2_DEVICE)
         assert K == len(self.ratios)
         return out
 

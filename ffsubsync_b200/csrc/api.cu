@@ -73,6 +73,11 @@ extern "C" int b2_create(int device, b2_handle* out) {
       delete h;
       return B2_ERR_CUDA;
     }
+  if (cudaEventCreateWithFlags(&h->resident_fence, cudaEventDisableTiming) != cudaSuccess ||
+      cudaEventCreateWithFlags(&h->resident_done, cudaEventDisableTiming) != cudaSuccess) {
+    delete h;
+    return B2_ERR_CUDA;
+  }
   h->log2_quirk_mask = compute_log2_quirk_mask();
   const char* acc = getenv("B2_ACC");  // A/B switch for profiling: "reg" keeps the accumulators in registers
   h->acc_in_tmem = !(acc && strcmp(acc, "reg") == 0);
@@ -83,6 +88,7 @@ extern "C" int b2_create(int device, b2_handle* out) {
 extern "C" int b2_destroy(b2_handle h) {
   if (!h) return B2_OK;
   DeviceScope scope(h->device);
+  if (h->stream2) cudaStreamSynchronize(h->stream2);
   cudaStreamSynchronize(h->stream);
   for (auto& w : h->ws)
     if (w.p) cudaFree(w.p);
@@ -110,6 +116,8 @@ extern "C" int b2_destroy(b2_handle h) {
     }
   for (auto& e : h->ev_pool)
     if (e) cudaEventDestroy(e);
+  if (h->resident_fence) cudaEventDestroy(h->resident_fence);
+  if (h->resident_done) cudaEventDestroy(h->resident_done);
   if (h->stream2) cudaStreamDestroy(h->stream2);
   if (h->own_stream && h->stream) cudaStreamDestroy(h->stream);
   delete h;
@@ -367,10 +375,13 @@ static int copy_out(b2_ctx* h, void* host, const void* dev, size_t bytes) {
   return B2_OK;
 }
 
-#define B2_ENTER(h)                                   \
-  if (!(h)) return B2_ERR_BAD_ARG;                    \
-  (h)->err.clear();                                   \
-  DeviceScope _b2_scope((h)->device);                 \
+#define B2_ENTER(h)                                              \
+  if (!(h)) return B2_ERR_BAD_ARG;                               \
+  (h)->err.clear();                                              \
+  const bool _b2_fence_was_valid = (h)->resident_fence_valid;    \
+  (void)_b2_fence_was_valid;                                     \
+  (h)->resident_fence_valid = false; /* any entry point breaks a chain of resident b2_sync_batch calls */ \
+  DeviceScope _b2_scope((h)->device);                            \
   if (!_b2_scope.ok) return B2_ERR_CUDA;
 
 // B2_DEVICE calls: a bulk pointer must be device (or managed) memory of the handle's device.
@@ -879,6 +890,8 @@ extern "C" int b2_sync_batch(b2_handle h, const int16_t* pcm, const int64_t* pcm
                              double* all_score, int32_t* all_offset, int memspace) {
   B2_ENTER(h);
   B2Range range("b2_sync_batch");
+  const bool resident = memspace == B2_DEVICE_RESIDENT;
+  if (resident) memspace = B2_DEVICE;
   if (B < 0 || K <= 0 || !pcm_off || !cue_off || !ratios)
     B2_FAIL(h, B2_ERR_BAD_ARG, "sync_batch: bad arguments");
   if (B == 0) return B2_OK;
@@ -909,7 +922,10 @@ extern "C" int b2_sync_batch(b2_handle h, const int16_t* pcm, const int64_t* pcm
   B2CueSource cue_src{cue_start_s, cue_end_s, cue_keep, cue_off, ratios, sample_rate, start_seconds};
 
   void *d_refsig, *d_subsig = nullptr, *d_res;
-  B2_TRY(b2i_ws(h, b2_ctx::WS_SIG_REF, (size_t)ref_off[B] * 4 + 64, &d_refsig));
+  // a chained resident call (see below) writes the buffer the previous call is not reading any more
+  const bool chained_candidate = resident && _b2_fence_was_valid;
+  const int refsig_slot = chained_candidate && h->refsig_parity == 0 ? b2_ctx::WS_SIG_REF2 : b2_ctx::WS_SIG_REF;
+  B2_TRY(b2i_ws(h, refsig_slot, (size_t)ref_off[B] * 4 + 64, &d_refsig));
   if (!fused) B2_TRY(b2i_ws(h, b2_ctx::WS_SIG_SUB, (size_t)sub_off[J] * 4 + 64, &d_subsig));
   B2_TRY(b2i_ws(h, b2_ctx::WS_MISC, J * 16 + (size_t)B * 16 + 256, &d_res));
   double* d_score = (double*)d_res;
@@ -1004,12 +1020,23 @@ extern "C" int b2_sync_batch(b2_handle h, const int16_t* pcm, const int64_t* pcm
       for (auto& e : tev) B2_CUDA(h, cudaEventCreate(&e));
       B2_CUDA(h, cudaEventRecord(tev[0], h->stream));
     }
+    // B2_DEVICE_RESIDENT, previous entry point on this handle = a pipelined resident b2_sync_batch: the VAD
+    // starts behind that call's fence (everything on the caller's stream up to, not including, its last
+    // correlation chain) and overlaps that chain like a further sub-batch - on vad_sms SMs if it is still running.
+    // It writes the other reference-signal buffer (the chain still reads the previous one); the chains of the
+    // call before that, which read this buffer, precede the fence.
+    const bool chained = chained_candidate;
+    bool prev_busy = false;
+    if (chained) {
+      prev_busy = cudaEventQuery(h->resident_done) == cudaErrorNotReady;
+      cudaGetLastError();
+    }
     {
       Stream2Scope on2(h);
-      B2_CUDA(h, cudaStreamWaitEvent(h->stream, inputs_ready, 0));
+      B2_CUDA(h, cudaStreamWaitEvent(h->stream, chained ? h->resident_fence : inputs_ready, 0));
       for (int i = 0; i < n_sub; ++i) {
         const int b0 = cut[i], b1 = cut[i + 1];
-        h->vad_partition_sms = i > 0 ? vad_sms : 0;
+        h->vad_partition_sms = (i > 0 || prev_busy) ? vad_sms : 0;
         if (trace) B2_CUDA(h, cudaEventRecord(tev[1 + 4 * i], h->stream));
         const int st = b1 > b0 ? b2i_vad_launch(h, d_pcm, pcm_off + b0, b1 - b0, fpw, non_speech_label,
                                                 (int64_t)fpw * energy_threshold, z_lo, z_hi, (float*)d_refsig,
@@ -1026,6 +1053,7 @@ extern "C" int b2_sync_batch(b2_handle h, const int16_t* pcm, const int64_t* pcm
     for (int i = 0; i < n_sub; ++i) {
       const int b0 = cut[i], b1 = cut[i + 1];
       const int nb = b1 - b0;
+      if (resident && i == n_sub - 1) B2_CUDA(h, cudaEventRecord(h->resident_fence, h->stream));
       B2_CUDA(h, cudaStreamWaitEvent(h->stream, vad_done[i], 0));
       if (trace) B2_CUDA(h, cudaEventRecord(tev[3 + 4 * i], h->stream));
       if (nb == 0) {
@@ -1052,6 +1080,11 @@ extern "C" int b2_sync_batch(b2_handle h, const int16_t* pcm, const int64_t* pcm
       if (trace) B2_CUDA(h, cudaEventRecord(tev[4 + 4 * i], h->stream));
       host_ms[i + 1] = host_now();
     }
+    if (resident) {
+      B2_CUDA(h, cudaEventRecord(h->resident_done, h->stream));
+      h->refsig_parity = refsig_slot == b2_ctx::WS_SIG_REF2 ? 1 : 0;
+      h->resident_fence_valid = true;
+    }
     if (trace) {
       B2_CUDA(h, cudaStreamSynchronize(h->stream2));
       B2_CUDA(h, cudaStreamSynchronize(h->stream));
@@ -1060,8 +1093,8 @@ extern "C" int b2_sync_batch(b2_handle h, const int16_t* pcm, const int64_t* pcm
         cudaEventElapsedTime(&ms, tev[0], tev[k]);
         return ms;
       };
-      fprintf(stderr, "[b2 pipe] B=%d n_sub=%d vad_sms=%d head_pct=%d corr_cap=%d; host: VADs enqueued at %.3f ms\n", B, n_sub,
-              vad_sms, head_pct, corr_cap, host_ms[0]);
+      fprintf(stderr, "[b2 pipe] B=%d n_sub=%d vad_sms=%d head_pct=%d corr_cap=%d chained=%d prev_busy=%d; host: VADs enqueued at %.3f ms\n",
+              B, n_sub, vad_sms, head_pct, corr_cap, (int)chained, (int)prev_busy, host_ms[0]);
       for (int i = 0; i < n_sub; ++i)
         fprintf(stderr, "[b2 pipe]  sub %d pairs %4d..%4d  VAD %7.3f -> %7.3f ms   chain %7.3f -> %7.3f ms   host enqueued chain at %.3f ms\n",
                 i, cut[i], cut[i + 1], at(1 + 4 * i), at(2 + 4 * i), at(3 + 4 * i), at(4 + 4 * i), host_ms[i + 1]);

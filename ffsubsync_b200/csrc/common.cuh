@@ -43,9 +43,16 @@ struct b2_ctx {
   int vad_ctas_per_sm = 0;       // 0 = as many as fit; set to 1 while b2_sync_batch pipelines
   int vad_partition_sms = 0;     // > 0: the VAD launches 512-consumer CTAs, one per SM, on this many SMs
   int corr_max_ctas = 0;         // > 0: persistent correlation kernels use at most this many CTAs
+  // B2_DEVICE_RESIDENT chaining of b2_sync_batch calls (api.cu): `resident_fence` is recorded on the caller's
+  // stream before the LAST sub-batch's correlation chain of a pipelined call, `resident_done` after it; the
+  // next resident call (if no other entry point ran in between: `resident_fence_valid`) starts its VAD behind
+  // the fence instead of behind the whole stream and writes the other reference-signal buffer
+  bool resident_fence_valid = false;
+  cudaEvent_t resident_fence = nullptr, resident_done = nullptr;
+  int refsig_parity = 0;
   // named grow-only workspaces
   enum { WS_STAGE_IN0, WS_STAGE_IN1, WS_STAGE_OUT, WS_META, WS_SPEC, WS_SCORES, WS_CAND,
-         WS_SIG_REF, WS_SIG_SUB, WS_MISC, WS_COUNTERS, WS_COUNT };
+         WS_SIG_REF, WS_SIG_REF2, WS_SIG_SUB, WS_MISC, WS_COUNTERS, WS_COUNT };
   DeviceBuf ws[WS_COUNT];
   HostBuf pinned[4];
   cudaEvent_t pinned_ev[4] = {};   // recorded after the last async copy out of pinned[i]

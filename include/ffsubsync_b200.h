@@ -44,7 +44,16 @@ typedef enum {
   B2_ERR_UNSUPPORTED = -6
 } b2_status;
 
-enum { B2_HOST = 0, B2_DEVICE = 1 };
+enum {
+  B2_HOST = 0,
+  B2_DEVICE = 1,
+  /* b2_sync_batch only: B2_DEVICE, plus the caller's promise that the INPUT arrays (pcm) are resident -
+     not written by anything queued on the handle's stream before this call.  The call may then start
+     reading them (its VAD runs on an internal stream) while the tail of the previous b2_sync_batch call
+     on this handle is still computing; outputs stay ordered on the handle's stream as with B2_DEVICE,
+     results are identical.  Back-to-back batches of a resident corpus: DESIGN.md section 4 K1p. */
+  B2_DEVICE_RESIDENT = 2
+};
 
 /* Per-(pair, ratio) status written by the aligner. */
 enum {

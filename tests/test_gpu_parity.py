@@ -995,6 +995,47 @@ def test_sync_batch_config3_256_pairs_vs_oracle(handle):
     torch.cuda.empty_cache()
 
 
+def test_sync_batch_resident_chained_calls_equal_ordered_calls(handle):
+    """B2_DEVICE_RESIDENT: back-to-back b2_sync_batch calls over resident corpora overlap (the VAD of call
+    m starts behind call m-1's fence and writes the other reference-signal buffer).  Two corpora of
+    different sizes, alternated without any synchronisation, must give exactly what ordered B2_DEVICE
+    calls give; an entry point in between (b2_synchronize) breaks the chain and the next call falls
+    back to stream order."""
+    import torch
+    from ffsubsync_b200 import _native
+    from ffsubsync_b200.batch import BatchSynchronizer
+    from ffsubsync_b200.synth import BENCH_RATIOS, make_pairs
+    bs = BatchSynchronizer(BENCH_RATIOS, 16000, 100, 0.0, max_offset_seconds=60)
+    corpora = []
+    for seed0, B in ((100, 120), (900, 100)):
+        pairs = make_pairs([seed0 + b for b in range(B)], 600.0, BENCH_RATIOS, handle=bs.handle)
+        n_win = int(pairs.win_off[-1])
+        cls_d = torch.from_numpy(pairs.window_class).cuda()
+        pcm = torch.empty(n_win * 160, dtype=torch.int16, device="cuda")
+        bs.handle.synth_pcm(cls_d.data_ptr(), n_win, 160, seed0, out=pcm.data_ptr(), memspace=_native.B2_DEVICE)
+        bs.handle.synchronize()
+        args = (pcm, pairs.win_off * 160, pairs.cue_start, pairs.cue_end, pairs.cue_off)
+        want = bs.sync_device(*args)
+        bs.handle.synchronize()
+        torch.cuda.synchronize()
+        want = {k: v.clone() for k, v in want.items()}
+        assert (want["best_offset"].cpu().numpy() == pairs.true_offset).all()
+        assert (want["best_k"].cpu().numpy() == pairs.true_k).all()
+        corpora.append((args, want))
+    order = [0, 1, 0, 0, 1, 1, 0, 1]
+    outs = [bs.sync_device(*corpora[c][0], inputs_resident=True) for c in order]   # nothing synchronised in between
+    bs.handle.synchronize()                                                         # breaks the chain
+    outs.append(bs.sync_device(*corpora[0][0], inputs_resident=True))               # unchained resident call
+    outs.append(bs.sync_device(*corpora[1][0], inputs_resident=True))               # chained again
+    outs.append(bs.sync_device(*corpora[0][0]))                                     # ordered call after a chained one
+    bs.handle.synchronize()
+    torch.cuda.synchronize()
+    for c, got in zip(order + [0, 1, 0], outs):
+        want = corpora[c][1]
+        for k in ("best_score", "best_offset", "best_k"):
+            assert torch.equal(got[k], want[k]), (c, k)
+
+
 def test_candidate_sharded_mode_single_rank_equals_sync_batch(handle):
     """The B < G mode's compute path (VAD -> own candidates -> reduce) with world = 1 equals
     b2_sync_batch; the multi-rank exchange is covered by the gloo test and tools/candidate_mode_bench.py."""

@@ -37,20 +37,21 @@ def main():
     del cls_d
     pcm_off = pairs.win_off * FPW
 
-    def run(env, steps=5):
+    def run(env, steps=5, resident=False):
         for k in KNOBS:
             os.environ.pop(k, None)
         os.environ.update(env)
+        kw = {"inputs_resident": True} if resident else {}
         out = {"best_score": torch.empty(B, dtype=torch.float64, device=dev),
                "best_offset": torch.empty(B, dtype=torch.int32, device=dev),
                "best_k": torch.empty(B, dtype=torch.int32, device=dev)}
         for _ in range(3):
-            bs.sync_device(pcm, pcm_off, pairs.cue_start, pairs.cue_end, pairs.cue_off, out=out)
+            bs.sync_device(pcm, pcm_off, pairs.cue_start, pairs.cue_end, pairs.cue_off, out=out, **kw)
         torch.cuda.synchronize()
         a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         a.record(stream)
         for _ in range(steps):
-            bs.sync_device(pcm, pcm_off, pairs.cue_start, pairs.cue_end, pairs.cue_off, out=out)
+            bs.sync_device(pcm, pcm_off, pairs.cue_start, pairs.cue_end, pairs.cue_off, out=out, **kw)
         b.record(stream)
         torch.cuda.synchronize()
         return a.elapsed_time(b) / steps, {k: v.cpu().numpy().copy() for k, v in out.items()}
@@ -66,6 +67,18 @@ def main():
     same = all(np.array_equal(ref[k], got[k]) for k in ref)
     print("library defaults: %.3f ms/step (%.0f alignments/s, %.3f x), identical=%s"
           % (ms2, B / ms2 * 1e3, ms0 / ms2, same), flush=True)
+    for steps in (5, 20):
+        ms3, got = run({}, steps=steps, resident=True)
+        same = all(np.array_equal(ref[k], got[k]) for k in ref)
+        print("library defaults, B2_DEVICE_RESIDENT (calls chained), %d steps: %.3f ms/step (%.0f alignments/s, %.3f x), identical=%s"
+              % (steps, ms3, B / ms3 * 1e3, ms0 / ms3, same), flush=True)
+    if os.environ.get("PIPE_PROBE") == "resident":
+        for env in ({"B2_VAD_SMS": "74"}, {"B2_VAD_SMS": "86"}, {"B2_SUBBATCHES": "2"}, {"B2_SUBBATCHES": "4"}):
+            ms3, got = run(env, steps=20, resident=True)
+            same = all(np.array_equal(ref[k], got[k]) for k in ref)
+            print("resident, %s: %.3f ms/step (%.0f alignments/s, %.3f x), identical=%s"
+                  % (env, ms3, B / ms3 * 1e3, ms0 / ms3, same), flush=True)
+        return
     combos = []
     for sub, sms in ((2, 80), (3, 80), (4, 80)):
         combos.append({"B2_SUBBATCHES": str(sub), "B2_VAD_SMS": str(sms), "B2_VAD_BATCH": "5", "B2_VAD_EVICT_FIRST": "1"})
