@@ -182,7 +182,8 @@ int b2_reduce_ratios(b2_handle h, const double* score, const int32_t* offset,
 
 /* ---- the whole hot path for a batch of (video, subtitle) pairs -----------------------------
  * VAD on each pair's PCM -> rasterise its cues at K ratios -> align -> reduce
- * (ffsubsync/ffsubsync.py:637 + :196-235).  pcm and the outputs follow memspace. */
+ * (ffsubsync/ffsubsync.py:637 + :196-235).  pcm and the outputs follow memspace; memspace may also be
+ * B2_DEVICE_RESIDENT (see the enum): consecutive calls over resident PCM then overlap across the call boundary. */
 int b2_sync_batch(b2_handle h, const int16_t* pcm, const int64_t* pcm_off, int B,
                   int frame_rate, int sample_rate, float non_speech_label,
                   int64_t energy_threshold, int z_lo, int z_hi,
