@@ -400,8 +400,12 @@ static int check_device_ptr(b2_ctx* h, const void* p, const char* what) {
             h->device);
   return B2_OK;
 }
-#define B2_CHECK_DEV(h, memspace, p, what) \
-  if ((memspace) == B2_DEVICE) B2_TRY(check_device_ptr(h, p, what))
+#define B2_CHECK_DEV(h, memspace, p, what)                                                       \
+  do {                                                                                           \
+    if ((memspace) != B2_HOST && (memspace) != B2_DEVICE) /* b2_sync_batch maps RESIDENT first */ \
+      B2_FAIL(h, B2_ERR_BAD_ARG, "%s: memspace must be B2_HOST or B2_DEVICE", what);             \
+    if ((memspace) == B2_DEVICE) B2_TRY(check_device_ptr(h, p, what));                           \
+  } while (0)
 
 // ---- VAD -----------------------------------------------------------------------------------
 extern "C" int b2_vad_frames_per_window(int frame_rate, int sample_rate) {

@@ -1036,6 +1036,18 @@ def test_sync_batch_resident_chained_calls_equal_ordered_calls(handle):
             assert torch.equal(got[k], want[k]), (c, k)
 
 
+def test_resident_memspace_is_sync_batch_only(handle):
+    """B2_DEVICE_RESIDENT is a promise about b2_sync_batch's inputs; every other entry point rejects it."""
+    import torch
+    from ffsubsync_b200 import _native
+    pcm = torch.zeros(16000, dtype=torch.int16, device="cuda")
+    out = torch.zeros(100, dtype=torch.float32, device="cuda")
+    with pytest.raises(_native.NativeError) as ei:
+        handle.vad_energy_zcr(pcm.data_ptr(), [0, 16000], 16000, 100, 0.0, 100000, out=out.data_ptr(),
+                              memspace=_native.B2_DEVICE_RESIDENT)
+    assert "memspace" in str(ei.value)
+
+
 def test_candidate_sharded_mode_single_rank_equals_sync_batch(handle):
     """The B < G mode's compute path (VAD -> own candidates -> reduce) with world = 1 equals
     b2_sync_batch; the multi-rank exchange is covered by the gloo test and tools/candidate_mode_bench.py."""

@@ -39,6 +39,10 @@ def test_library_exports_every_header_symbol(built):
     assert _native.load().b2_version() == 200
     # every declaration cites the reference interface it replaces
     assert header.count("ffsubsync/") >= 8
+    # memspace values of the binding == the header's enum
+    for name in ("B2_HOST", "B2_DEVICE", "B2_DEVICE_RESIDENT"):
+        m = re.search(r"\b%s\s*=\s*(\d+)" % name, header)
+        assert m and int(m.group(1)) == getattr(_native, name), name
 
 
 def test_pure_host_entry_points(built):
